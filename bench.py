@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric (cell-steps/sec of the stable-fluids scene step) on B200.
+
+A "step" is one SCENE STEP = 1x FluidSim::step (src/lib.rs:267) + 1x DensitySim::step
+(src/lib.rs:226) over one w x h grid, K=20 Jacobi sweeps per lin_solve (src/lib.rs:52), i.e.
+40 pressure sweeps per step -- BASELINE.json configs[2] (4096x4096, the roofline headline).
+cell-steps/s = w*h*steps / seconds (border cells included, like the constructor arguments).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--size 4096]
+
+Prints ONE JSON line on rank 0.  Keys (see the task contract): value = device-timed
+throughput with all fields resident in HBM; e2e = the same metric through the crate-API
+mirror with HOST buffers (h2d of the three source fields + d2h of the density every step);
+roofline = the dominant kernel against the measured HBM peak; cpu_baseline = the CPU oracle
+(faithful loop order, 1 thread, like the single-threaded reference) on a bounded sample.
+--impl reference times that CPU path alone (the Rust reference itself cannot be built in
+this image: no rustc/cargo, un-vendored deps).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DT, VISC, DIFF, ITERS = 1e-2, 1e-6, 1e-6, 20
+SEED = 0x5EED0001
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic scene: Taylor-Green velocity at CFL ~ 2 cells + hash noise,
+# Gaussian dye blob + noise.  Deterministic in the GLOBAL cell index, so any slab of it can be
+# generated independently (multi-GPU ranks see identical data).
+# ------------------------------------------------------------------------------------------
+def _splitmix64(z):
+    z = (z + np.uint64(0x9E3779B97F4A7C15)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & np.uint64(0xFFFFFFFFFFFFFFFF)
+    return z ^ (z >> np.uint64(31))
+
+
+def noise(field: int, w: int, y0: int, y1: int) -> np.ndarray:
+    """r in [-1, 1), exactly representable: ((splitmix64(seed ^ field<<56 ^ idx) >> 40) * 2^-24)*2 - 1."""
+    with np.errstate(over="ignore"):
+        idx = (np.arange(y0, y1, dtype=np.uint64)[:, None] * np.uint64(w) + np.arange(w, dtype=np.uint64)[None, :])
+        z = _splitmix64(idx ^ np.uint64(SEED) ^ (np.uint64(field) << np.uint64(56)))
+    return ((z >> np.uint64(40)).astype(np.float32) * np.float32(2.0 ** -24)) * np.float32(2.0) - np.float32(1.0)
+
+
+def make_scene(w: int, h: int, y0: int = 0, y1: int | None = None, cfl: float = 2.0):
+    """Rows [y0, y1) of the global w x h scene: dict of float32 (rows, w) arrays."""
+    y1 = h if y1 is None else y1
+    amp = np.float32(cfl / (DT * (w - 2)))
+    xh = (np.arange(w, dtype=np.float32) / np.float32(w))[None, :]
+    yh = (np.arange(y0, y1, dtype=np.float32) / np.float32(h))[:, None]
+    two_pi = np.float32(2 * np.pi)
+    u = amp * np.sin(two_pi * xh) * np.cos(two_pi * yh) + np.float32(1e-3) * noise(0, w, y0, y1)
+    v = -amp * np.cos(two_pi * xh) * np.sin(two_pi * yh) + np.float32(1e-3) * noise(1, w, y0, y1)
+    sig = np.float32(w / 16.0)
+    dx = np.arange(w, dtype=np.float32)[None, :] - np.float32(w / 2)
+    dy = np.arange(y0, y1, dtype=np.float32)[:, None] - np.float32(h / 2)
+    dens = np.exp(-(dx * dx + dy * dy) / (np.float32(2.0) * sig * sig)).astype(np.float32) \
+        + np.float32(1e-3) * noise(2, w, y0, y1)
+    z = np.zeros((y1 - y0, w), np.float32)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    # u_prev / v_prev / dens_prev are the per-step SOURCE fields (uv_mut / density_mut)
+    return {"u": f32(u), "v": f32(v), "u_prev": f32(np.float32(1e-2) * noise(3, w, y0, y1)),
+            "v_prev": f32(np.float32(1e-2) * noise(4, w, y0, y1)), "dens": f32(dens),
+            "dens_prev": f32(np.float32(1e-2) * (noise(5, w, y0, y1) + np.float32(1.0))), "zero": z}
+
+
+def bytes_per_cell_step(k: int = ITERS) -> int:
+    """Algorithmic HBM bytes per cell per scene step: 188 + 60K."""
+    return 188 + 60 * k
+
+
+# ------------------------------------------------------------------------------------------
+# clocks (sampled DURING the timed region)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # NVML unavailable: report nulls rather than fail the bench
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self._nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        return {"sm_mhz": (float(np.median(self.samples)) if self.samples else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU path (the oracle = restatement of the reference; used ONLY as baseline / reference arm)
+# ------------------------------------------------------------------------------------------
+def cpu_scene_steps(w: int, rows: int, steps: int, warmup: int = 0):
+    """Times `steps` scene steps of the faithful-order, single-thread oracle on a w x rows grid
+    (a bounded sample of the w x w workload).  Returns (cell_steps_per_s, seconds_per_step)."""
+    import oracle
+    oracle.build()
+    try:
+        os.sched_setaffinity(0, {sorted(os.sched_getaffinity(0))[0]})  # pin: the reference is single-threaded
+    except Exception:
+        pass
+    sc = make_scene(w, rows)
+    f = oracle.Fluid(w, rows, iters=ITERS, order=oracle.FAITHFUL, openmp=False)
+    d = oracle.Density(w, rows, iters=ITERS, order=oracle.FAITHFUL, openmp=False)
+    f.u[:], f.v[:], f.u_prev[:], f.v_prev[:] = sc["u"], sc["v"], sc["u_prev"], sc["v_prev"]
+    d.dens[:], d.dens_prev[:] = sc["dens"], sc["dens_prev"]
+    for _ in range(warmup):
+        f.step(DT, VISC)
+        d.step((f.u, f.v), DT, DIFF)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        f.step(DT, VISC)
+        d.step((f.u, f.v), DT, DIFF)
+    sec = (time.perf_counter() - t0) / max(steps, 1)
+    return w * rows / sec, sec
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; 1 thread
+    because src/lib.rs is single-threaded), same metric/config, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = args.size
+    total = args.steps + args.warmup
+    rows = 1024 if total <= 8 else (512 if total <= 16 else 256)
+    rows = min(rows, w)
+    value, sec = cpu_scene_steps(w, rows, args.steps, args.warmup)
+    sample = (f"each step = 1 scene step (K={ITERS}, D=1) of the faithful-order C oracle on a {w}x{rows} grid "
+              f"(1/{w // rows} of the {w}x{w} workload), 1 thread pinned; the Rust reference cannot be built here")
+    line = {
+        "impl": "reference", "metric": "cell-steps/sec", "value": value, "unit": "cell-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * (w / rows), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "cell-steps/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus):
+    w = args.size
+    return {"workload": f"{w}x{w} scene step: FluidSim::step + 1x DensitySim::step, K={ITERS} sweeps per lin_solve "
+                        f"(40 pressure sweeps/step), dt={DT}, visc={VISC}, diff={DIFF} (BASELINE.json configs[2])",
+            "grid": [w, w], "jacobi_iters": ITERS, "dyes": 1, "dt": DT, "visc": VISC, "diff": DIFF,
+            "init": "Taylor-Green velocity at CFL~2 cells + hash noise; Gaussian dye; noisy source fields",
+            "l2": f"inputs larger than L2 (8 fields x {w * w * 4 >> 20} MiB)", "parallelism": f"slab{n_gpus}"}
+
+
+# ------------------------------------------------------------------------------------------
+# B200 path
+# ------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import __graft_entry__
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; fruid_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if rank == 0:
+        __graft_entry__.build()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    import fruid_b200 as fb
+    from fruid_b200 import _lib
+    L = _lib.lib
+
+    w = h = args.size
+    if world > 1:
+        return run_b200_multi(args, fb, dist, rank, world, local)
+
+    sc = make_scene(w, h)
+    sim, den = fb.FluidSim(w, h), fb.DensitySim(w, h)
+    if args.fused is not None:
+        sim.set_fused_sweeps(args.fused)
+        den.set_fused_sweeps(args.fused)
+    for name, field in (("u", 0), ("v", 1), ("u_prev", 2), ("v_prev", 3)):
+        _lib.check(L.fruid_fluid_upload(sim._h, field, _lib.ptr(sc[name])))
+    for name, field in (("dens", 0), ("dens_prev", 1)):
+        _lib.check(L.fruid_density_upload(den._h, field, _lib.ptr(sc[name])))
+    stream = torch.cuda.ExternalStream(int(L.fruid_fluid_stream(sim._h)))
+
+    def scene_step():
+        _lib.check(L.fruid_fluid_step(sim._h, DT, VISC))
+        _lib.check(L.fruid_density_step_dev(den._h, sim._h, DT, DIFF))
+
+    # ---- device-resident throughput ("value") ----
+    for _ in range(args.warmup):
+        scene_step()
+    torch.cuda.synchronize()
+    n0 = fb.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(args.steps):
+            scene_step()
+        e1.record(stream)   # density work is ordered before this by the cross-stream events
+        torch.cuda.synchronize()
+    launches = fb.launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    ms_per_step = ms / args.steps
+    value = w * h * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel timing pass (roofline of the dominant kernel) ----
+    _lib.profile_enable(True)
+    for _ in range(max(2, min(args.steps, 5))):
+        scene_step()
+    stats = _lib.profile_report()
+    _lib.profile_enable(False)
+    tot_ms = sum(t for _, t in stats.values()) or 1.0
+    jac = {k: v for k, v in stats.items() if k.startswith("k_jacobi")}
+    dom_name = max(jac, key=lambda k: jac[k][1]) if jac else max(stats, key=lambda k: stats[k][1])
+    dom_launches, dom_ms = stats[dom_name]
+    sweeps_per_scene_step = 5 * ITERS
+    scene_steps_profiled = max(2, min(args.steps, 5))
+    sweeps_per_launch = sweeps_per_scene_step * scene_steps_profiled / dom_launches
+    alg_bytes_per_launch = 12.0 * w * h * sweeps_per_launch      # 12 B/cell/sweep
+    avg_s = dom_ms * 1e-3 / dom_launches
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes_per_launch / avg_s / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom_name)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                "sweeps_per_launch": sweeps_per_launch, "avg_launch_us": avg_s * 1e6,
+                "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                "kernel_share_of_step": dom_ms / tot_ms,
+                "kernels_ms_per_step": {k: round(t / scene_steps_profiled, 4) for k, (n, t) in sorted(stats.items())},
+                "step_effective_gbs": bytes_per_cell_step() * value / 1e9,
+                "step_effective_frac": bytes_per_cell_step() * value / 1e9 / peak}
+
+    # ---- end to end through the crate-API mirror with HOST buffers ----
+    e2e = run_e2e(args, fb, torch, sc, w, h)
+
+    # ---- CPU baseline beside it (bounded sample) ----
+    cpu = None
+    if not args.no_cpu:
+        rows = min(1024, h)
+        cv, csec = cpu_scene_steps(w, rows, 1)
+        cpu = {"value": cv, "unit": "cell-steps/s", "cores": 1, "kind": "port",
+               "sample": f"1 scene step (K={ITERS}, D=1) of the faithful-order C oracle on a {w}x{rows} grid "
+                         f"({csec:.1f} s), 1 thread pinned (the reference is single-threaded); "
+                         f"host has {os.cpu_count()} cores"}
+
+    line = {"metric": "cell-steps/sec", "value": value, "unit": "cell-steps/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1),
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "impl": "b200"}
+    print(json.dumps(line), flush=True)
+
+
+def run_e2e(args, fb, torch, sc, w, h):
+    """Scene step through FluidSim / DensitySim (the call a user makes) with host buffers: every
+    step rewrites the three source fields on the host (page-locked mirrors), which are uploaded by
+    step(), and reads the resulting density back to the host."""
+    from fruid_b200 import _lib
+    sim, den = fb.FluidSim(w, h), fb.DensitySim(w, h)
+    if args.fused is not None:
+        sim.set_fused_sweeps(args.fused)
+        den.set_fused_sweeps(args.fused)
+    for name, field in (("u", 0), ("v", 1)):
+        _lib.check(_lib.lib.fruid_fluid_upload(sim._h, field, _lib.ptr(sc[name])))
+    _lib.check(_lib.lib.fruid_density_upload(den._h, 0, _lib.ptr(sc["dens"])))
+    srcs = (sc["u_prev"].reshape(-1), sc["v_prev"].reshape(-1), sc["dens_prev"].reshape(-1))
+    nbytes = w * h * 4
+
+    def step():
+        u0, v0 = sim.uv_mut()
+        u0.copy_from(srcs[0])               # host writes into the pinned mirrors ...
+        v0.copy_from(srcs[1])
+        den.density_mut().copy_from(srcs[2])
+        sim.step(DT, VISC)                  # ... uploaded here (h2d inside the timed region)
+        den.step(sim.uv(), DT, DIFF)
+        return den.density().data()         # d2h of the step's result
+
+    # first call downloads stale mirrors once; warm up
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    n = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        out = step()
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    assert np.isfinite(out[:: max(1, out.size // 4096)]).all()
+    return {"value": w * h * n / sec, "unit": "cell-steps/s", "h2d_bytes_per_step": 3 * nbytes,
+            "d2h_bytes_per_step": nbytes, "steps": n,
+            "note": "per step: the u_prev, v_prev and dens_prev source fields are rewritten on the host (copy into "
+                    "the page-locked mirrors, inside the timed region) and uploaded by step(); density() is read "
+                    "back to the host; wall-clock over n steps, synchronised on both sides"}
+
+
+def run_b200_multi(args, fb, dist, rank, world, local):
+    raise SystemExit("multi-GPU slab path not built yet")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=4096)
+    ap.add_argument("--fused", type=int, default=None, help="Jacobi sweeps per launch (default: library choice)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,233 @@
+"""Python mirror of the reference crate API (src/lib.rs:1, 210-294) over the C ABI.
+
+Same names, argument order and semantics as the Rust types:
+
+    FluidSim.new(w, h) / FluidSim(w, h); .step(dt, visc); .uv(); .uv_mut(); .width(); .height()
+    DensitySim(w, h); .step((u, v), dt, diff); .density(); .density_mut()
+
+The fields live in HBM; the Array2D objects handed out are host mirrors that are
+downloaded lazily on first read and uploaded lazily before the next step when written.
+`DensitySim.step(sim.uv(), ...)` (src/main.rs:115) recognises the mirrors of a live
+FluidSim and uses its device-resident velocity instead of uploading it again.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib, ptr
+
+
+class Array2D:
+    """Host mirror of one device field: idek_basics::Array2D<f32> (src/lib.rs:1).
+
+    Indexed by (x, y) like the Rust type; flat layout x + y*width.  Reads download the
+    field if the host copy is stale; single-cell writes are forwarded as injections;
+    data_mut() marks the whole field dirty (re-uploaded before the next step).
+    """
+
+    def __init__(self, owner, field: int, width: int, height: int):
+        self._owner, self._field = owner, field
+        self._w, self._h = width, height
+        self._host = np.zeros((height, width), np.float32)
+        # page-lock the mirror (fixed length for the object's life) so transfers run at PCIe rate
+        self._pinned = lib.fruid_host_register(self._host.ctypes.data, self._host.nbytes) == 0
+        self._stale = False   # device newer than host
+        self._dirty = False   # host newer than device (whole field)
+        self._cells = []      # pending single-cell writes (x, y, value)
+
+    def __del__(self):
+        if getattr(self, "_pinned", False):
+            self._pinned = False
+            lib.fruid_host_unregister(self._host.ctypes.data)
+
+    def width(self) -> int:
+        return self._w
+
+    def height(self) -> int:
+        return self._h
+
+    # -- synchronisation ---------------------------------------------------------
+    def _pull(self):
+        if self._stale:
+            self._owner._download(self._field, self._host)
+            self._stale = False
+            for (x, y, val) in self._cells:  # keep not-yet-pushed writes visible
+                self._host[y, x] = val
+
+    def _push(self):
+        """Make the device copy current (called by the owner before a step)."""
+        if self._dirty:
+            self._owner._upload(self._field, self._host)
+        else:
+            for (x, y, val) in self._cells:
+                self._owner._inject(self._field, x, y, val)
+        self._dirty = False
+        self._cells = []
+
+    def _mark_stale(self):
+        self._stale, self._dirty, self._cells = True, False, []
+
+    # -- Rust-like surface --------------------------------------------------------
+    def data(self) -> np.ndarray:
+        """`data()`: flat read-only view, x fastest."""
+        self._pull()
+        v = self._host.reshape(-1).view()
+        v.flags.writeable = False
+        return v
+
+    def data_mut(self) -> np.ndarray:
+        """`data_mut()`: flat writable view; the field is re-uploaded before the next step."""
+        self._pull()
+        self._dirty = True
+        return self._host.reshape(-1)
+
+    def fill(self, val: float) -> None:
+        """`data_mut().fill(val)` (src/main.rs:105) without a download."""
+        self._host.fill(val)
+        self._stale, self._dirty, self._cells = False, True, []
+
+    def copy_from(self, src) -> None:
+        """`data_mut().copy_from_slice(src)`: overwrite the whole field (no download first)."""
+        np.copyto(self._host, np.asarray(src, np.float32).reshape(self._h, self._w))
+        self._stale, self._dirty, self._cells = False, True, []
+
+    def __getitem__(self, pos):
+        x, y = pos
+        self._pull()
+        return self._host[y, x]
+
+    def __setitem__(self, pos, val):
+        x, y = pos
+        if not (0 <= x < self._w and 0 <= y < self._h):
+            raise IndexError(f"({x}, {y}) outside {self._w}x{self._h}")  # Rust panics
+        val = np.float32(val)
+        if not self._stale:
+            self._host[y, x] = val
+        if not self._dirty:
+            self._cells.append((int(x), int(y), float(val)))
+
+    def numpy(self) -> np.ndarray:
+        """(height, width) float32 copy of the current contents."""
+        self._pull()
+        return self._host.copy()
+
+
+class FluidSim:
+    """src/lib.rs:247-294."""
+
+    def __init__(self, width: int, height: int):
+        self._h = _lib._vp()
+        check(lib.fruid_fluid_create(width, height, _lib.ctypes.byref(self._h)))
+        self._w_, self._h_ = int(width), int(height)
+        self._u = Array2D(self, _lib.U, width, height)
+        self._v = Array2D(self, _lib.V, width, height)
+        self._u_prev = Array2D(self, _lib.U_PREV, width, height)
+        self._v_prev = Array2D(self, _lib.V_PREV, width, height)
+
+    new = classmethod(lambda cls, width, height: cls(width, height))  # FluidSim::new, lib.rs:256
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.fruid_fluid_destroy(h)
+
+    # transfers used by the mirrors
+    def _download(self, field, host):
+        check(lib.fruid_fluid_download(self._h, field, ptr(host)))
+
+    def _upload(self, field, host):
+        check(lib.fruid_fluid_upload(self._h, field, ptr(host)))
+
+    def _inject(self, field, x, y, val):
+        check(lib.fruid_fluid_inject(self._h, field, x, y, val))
+
+    def set_iterations(self, k: int) -> None:
+        """Sweeps per lin_solve (reference: 20, src/lib.rs:52).  Extension."""
+        check(lib.fruid_fluid_set_iterations(self._h, k))
+
+    def set_fused_sweeps(self, t: int) -> None:
+        check(lib.fruid_fluid_set_fused_sweeps(self._h, t))
+
+    def step(self, dt: float, visc: float) -> None:  # lib.rs:267
+        for a in (self._u, self._v, self._u_prev, self._v_prev):
+            a._push()
+        check(lib.fruid_fluid_step(self._h, dt, visc))
+        for a in (self._u, self._v, self._u_prev, self._v_prev):
+            a._mark_stale()
+
+    def uv(self):  # lib.rs:279
+        return (self._u, self._v)
+
+    def uv_mut(self):  # lib.rs:283 -- (u_prev, v_prev): sources in, pressure/divergence out
+        return (self._u_prev, self._v_prev)
+
+    def width(self) -> int:  # lib.rs:287
+        return self._w_
+
+    def height(self) -> int:  # lib.rs:291
+        return self._h_
+
+    def sync(self) -> None:
+        check(lib.fruid_fluid_sync(self._h))
+
+
+class DensitySim:
+    """src/lib.rs:210-245."""
+
+    def __init__(self, width: int, height: int):
+        self._h = _lib._vp()
+        check(lib.fruid_density_create(width, height, _lib.ctypes.byref(self._h)))
+        self._w_, self._h_ = int(width), int(height)
+        self._dens = Array2D(self, _lib.DENS, width, height)
+        self._dens_prev = Array2D(self, _lib.DENS_PREV, width, height)
+
+    new = classmethod(lambda cls, width, height: cls(width, height))  # lib.rs:217
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.fruid_density_destroy(h)
+
+    def _download(self, field, host):
+        check(lib.fruid_density_download(self._h, field, ptr(host)))
+
+    def _upload(self, field, host):
+        check(lib.fruid_density_upload(self._h, field, ptr(host)))
+
+    def _inject(self, field, x, y, val):
+        check(lib.fruid_density_inject(self._h, field, x, y, val))
+
+    def set_iterations(self, k: int) -> None:
+        check(lib.fruid_density_set_iterations(self._h, k))
+
+    def set_fused_sweeps(self, t: int) -> None:
+        check(lib.fruid_density_set_fused_sweeps(self._h, t))
+
+    def step(self, uv, dt: float, diff: float) -> None:  # lib.rs:226 (uv first, then dt, diff)
+        u, v = uv
+        self._dens._push()
+        self._dens_prev._push()
+        sim = getattr(u, "_owner", None)
+        if (isinstance(u, Array2D) and isinstance(v, Array2D) and isinstance(sim, FluidSim)
+                and v._owner is sim and u._field == _lib.U and v._field == _lib.V):
+            u._push()
+            v._push()
+            check(lib.fruid_density_step_dev(self._h, sim._h, dt, diff))
+        else:
+            un = np.ascontiguousarray(u.numpy() if isinstance(u, Array2D) else u, np.float32)
+            vn = np.ascontiguousarray(v.numpy() if isinstance(v, Array2D) else v, np.float32)
+            if un.shape != (self._h_, self._w_) or vn.shape != (self._h_, self._w_):
+                raise _lib.FruidError(_lib.ERR_SIZE_MISMATCH, "velocity shape does not match the density grid")
+            check(lib.fruid_density_step_host(self._h, ptr(un), ptr(vn), dt, diff))
+        self._dens._mark_stale()
+        self._dens_prev._mark_stale()
+
+    def density(self) -> Array2D:  # lib.rs:238
+        return self._dens
+
+    def density_mut(self) -> Array2D:  # lib.rs:242 -- dens_prev (the source), not dens
+        return self._dens_prev
+
+    def sync(self) -> None:
+        check(lib.fruid_density_sync(self._h))

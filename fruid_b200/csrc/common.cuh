@@ -1,0 +1,71 @@
+// common.cuh -- arithmetic and boundary helpers shared by every kernel.
+//
+// Bit-exactness contract: the reference (Rust, src/lib.rs) uses only
+// IEEE-754 binary32 + - * / with no FMA contraction and no reassociation.  All
+// arithmetic below goes through the round-to-nearest intrinsics, which nvcc never
+// contracts or reorders; the library is additionally built with -fmad=false and
+// without --use_fast_math (default -prec-div=true -ftz=false).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace fruid {
+
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+enum : int { B_POSITIVE = 0, B_NEGX = 1, B_NEGY = 2 };  // enum Bounds, src/lib.rs:19-25
+
+// Grid geometry: w x h cells including the border, rows of `pitch` floats.
+struct Geom {
+    int w, h;       // total size (constructor arguments of FluidSim::new)
+    int nx, ny;     // interior size, src/lib.rs:12-17
+    size_t pitch;   // floats per device row (multiple of 32 for library-owned fields)
+};
+
+__host__ __device__ __forceinline__ Geom make_geom(size_t w, size_t h, size_t pitch) {
+    Geom g;
+    g.w = (int)w; g.h = (int)h; g.nx = (int)w - 2; g.ny = (int)h - 2; g.pitch = pitch;
+    return g;
+}
+
+__device__ __forceinline__ size_t at(const Geom& g, int x, int y) { return (size_t)x + (size_t)y * g.pitch; }
+
+__device__ __forceinline__ float sgn(bool neg, float v) { return neg ? -v : v; }
+
+// set_bnd (src/lib.rs:27-44) folded into the producer: the thread that owns interior
+// cell (i, j) with new value v also writes every border cell that mirrors it.
+//   x[0,j]   = sx*x[1,j]      x[nx+1,j] = sx*x[nx,j]      (sx = -1 iff NegX)   lib.rs:31-32
+//   x[i,0]   = sy*x[i,1]      x[i,ny+1] = sy*x[i,ny]      (sy = -1 iff NegY)   lib.rs:36-37
+//   corner   = 0.5*(row-edge + col-edge) = 0.5*(sy*v + sx*v), v = diagonal interior cell
+//                                                                              lib.rs:40-43
+// Valid for nx >= 1 and ny >= 1 (for nx == 0 or ny == 0 set_bnd has sequential
+// dependencies; those sizes take the serial kernel in serial.cuh).
+__device__ __forceinline__ void store_with_bnd(float* __restrict__ out, const Geom& g, int b, int i, int j,
+                                               float v) {
+    out[at(g, i, j)] = v;
+    const bool nxg = (b == B_NEGX), nyg = (b == B_NEGY);
+    const bool xl = (i == 1), xr = (i == g.nx), yt = (j == 1), yb = (j == g.ny);
+    if (xl | xr | yt | yb) {
+        const float vx = sgn(nxg, v), vy = sgn(nyg, v);
+        if (xl) out[at(g, 0, j)] = vx;
+        if (xr) out[at(g, g.nx + 1, j)] = vx;
+        if (yt) out[at(g, i, 0)] = vy;
+        if (yb) out[at(g, i, g.ny + 1)] = vy;
+        const float c = fmul(0.5f, fadd(vy, vx));
+        if (xl && yt) out[at(g, 0, 0)] = c;
+        if (xl && yb) out[at(g, 0, g.ny + 1)] = c;
+        if (xr && yt) out[at(g, g.nx + 1, 0)] = c;
+        if (xr && yb) out[at(g, g.nx + 1, g.ny + 1)] = c;
+    }
+}
+
+// mix(), src/lib.rs:80-82: (1 - t)*a + t*b, unfused.
+__device__ __forceinline__ float mixf(float a, float b, float t) {
+    return fadd(fmul(fsub(1.0f, t), a), fmul(t, b));
+}
+
+}  // namespace fruid

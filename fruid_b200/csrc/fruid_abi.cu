@@ -1,0 +1,566 @@
+// fruid_abi.cu -- the C ABI of include/fruid_b200.h: device twins of FluidSim /
+// DensitySim (reference src/lib.rs:210-294), the step schedules vel_step / dens_step
+// (src/lib.rs:171-208) and the per-operator entry points.  No CPU fallback anywhere:
+// every entry point either runs the CUDA kernels or returns an error.
+#include "../../include/fruid_b200.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_basic.cuh"
+#include "kernels_serial.cuh"
+#include "jacobi_tile.cuh"
+
+using namespace fruid;
+
+// --------------------------------------------------------------------------------------
+// errors, launch accounting
+// --------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(e_ == cudaErrorMemoryAllocation ? FRUID_ERR_OOM : FRUID_ERR_CUDA,         \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define TRY(call)              \
+    do {                       \
+        int r_ = (call);       \
+        if (r_ != 0) return r_; \
+    } while (0)
+// Optional per-kernel timing (bench.py roofline leg): every launch is bracketed by CUDA
+// events on the launching stream; fruid_profile_report() synchronises and sums by name.
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+static inline void prof_pre(cudaStream_t st) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r{nullptr, prof_event(), nullptr};
+    cudaEventRecord(r.e0, st);
+    g_prof.push_back(r);
+}
+static inline int launched(const char* what, cudaStream_t st) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (g_prof_on) {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        if (!g_prof.empty() && g_prof.back().name == nullptr) {
+            g_prof.back().name = what;
+            g_prof.back().e1 = prof_event();
+            cudaEventRecord(g_prof.back().e1, st);
+        }
+    }
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return fail(FRUID_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+#define LAUNCH(name, st, ...)        \
+    do {                             \
+        prof_pre(st);                \
+        __VA_ARGS__;                 \
+        TRY(launched(name, st));     \
+    } while (0)
+
+extern "C" int fruid_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+    return 0;
+}
+extern "C" int fruid_profile_report(fruid_kernel_stat* out, size_t cap, size_t* n_out) {
+    if (!n_out) return fail(FRUID_ERR_BAD_ARG, "null n_out");
+    CU(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    size_t n = 0;
+    for (const ProfRec& r : g_prof) {
+        if (r.name && r.e1) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+                size_t k = 0;
+                for (; k < n; ++k) if (strncmp(out[k].name, r.name, sizeof out[k].name) == 0) break;
+                if (k == n && n < cap) { memset(&out[n], 0, sizeof out[n]); strncpy(out[n].name, r.name, sizeof out[n].name - 1); ++n; }
+                if (k < cap) { out[k].launches += 1; out[k].total_ms += ms; }
+            }
+        }
+        if (r.e0) g_prof_pool.push_back(r.e0);
+        if (r.e1) g_prof_pool.push_back(r.e1);
+    }
+    g_prof.clear();
+    *n_out = n;
+    return 0;
+}
+
+extern "C" const char* fruid_last_error(void) { return g_err; }
+extern "C" uint64_t fruid_kernel_launch_count(void) { return g_launches.load(); }
+extern "C" const char* fruid_build_info(void) { return "fruid_b200 0.1 (sm_100a, -fmad=false, IEEE f32 rn)"; }
+
+// --------------------------------------------------------------------------------------
+// operator launchers on device buffers
+// --------------------------------------------------------------------------------------
+static inline size_t pitch_for(size_t w) { return (w + 31) / 32 * 32; }
+static inline bool degenerate(const Geom& g) { return g.nx < 1 || g.ny < 1; }
+static inline dim3 cell_block() { return dim3(128, 2); }
+static inline dim3 cell_grid(int cx, int cy) { return dim3((cx + 127) / 128, (cy + 1) / 2); }
+
+static int op_add_source(float* x1, const float* s1, float* x2, const float* s2, const Geom& g, float dt,
+                         cudaStream_t st) {
+    LAUNCH("k_add_source", st, k_add_source<<<cell_grid(g.w, g.h), cell_block(), 0, st>>>(x1, s1, x2, s2, g, dt));
+    return 0;
+}
+
+static int op_set_bnd(int b, float* x, const Geom& g, cudaStream_t st) {
+    if (degenerate(g)) {
+        LAUNCH("k_serial_set_bnd", st, k_serial_set_bnd<<<1, 1, 0, st>>>(x, g, b));
+        return 0;
+    }
+    LAUNCH("k_set_bnd", st, k_set_bnd<<<cell_grid(g.nx, g.ny), cell_block(), 0, st>>>(x, g, b));
+    return 0;
+}
+
+// lin_solve, src/lib.rs:46-71.  x / scratch ping-pong like the re-bound references at
+// lib.rs:49-50,68.  `x` and `scratch` are passed by reference: on return `x` names the
+// buffer holding the newest iterate (the two are exchanged when the number of launches
+// is odd), so the caller's field roles follow the data and nothing is copied.
+// fused = sweeps per launch (1 = k_jacobi1; >1 = register-tile kernel of jacobi_tile.cuh).
+static int op_lin_solve(int b, float*& x, const float* x0, float*& scratch, const Geom& g, float a, float c,
+                        int iters, int fused, cudaStream_t st) {
+    if (iters < 2 || (iters & 1)) return fail(FRUID_ERR_ODD_ITERATIONS, "iterations must be even and >= 2, got %d", iters);
+    if (degenerate(g)) {
+        LAUNCH("k_serial_lin_solve", st, k_serial_lin_solve<<<1, 1, 0, st>>>(x, x0, scratch, g, a, c, b, iters));
+        return 0;
+    }
+    if (fused <= 0) fused = jacobi_tile_default_fused(g, iters);
+    if (fused > iters) fused = iters;
+    if (fused == 1) {
+        for (int it = 0; it < iters; ++it) {
+            LAUNCH("k_jacobi1", st, k_jacobi1<<<cell_grid(g.nx, g.ny), cell_block(), 0, st>>>(scratch, x, x0, g, a, c, b));
+            float* t = x; x = scratch; scratch = t;
+        }
+        return 0;
+    }
+    const int nblocks = (iters + fused - 1) / fused;
+    int done = 0;
+    for (int k = 0; k < nblocks; ++k) {
+        const int T = (iters - done + (nblocks - k) - 1) / (nblocks - k);  // spread evenly
+        LAUNCH("k_jacobi_tile", st, TRY(jacobi_tile_launch(scratch, x, x0, g, a, c, b, T, st)));
+        done += T;
+        float* t = x; x = scratch; scratch = t;
+    }
+    return 0;
+}
+
+// diffuse, src/lib.rs:73-78: a = ((dt*diff)*nx)*ny in f32, c = 1 + 4a.
+static int op_diffuse(int b, float*& x, const float* x0, float*& scratch, const Geom& g, float diff, float dt,
+                      int iters, int fused, cudaStream_t st) {
+    const float a = ((dt * diff) * (float)g.nx) * (float)g.ny;
+    const float c = 1.0f + 4.0f * a;
+    return op_lin_solve(b, x, x0, scratch, g, a, c, iters, fused, st);
+}
+
+// advect, src/lib.rs:84-126, for 1 or 2 fields sharing the back-trace.
+static int op_advect(int nf, float* const* d, const float* const* d0, const int* b, const float* u, const float* v,
+                     const Geom& g, float dt, cudaStream_t st) {
+    const float dt0 = dt * (float)g.nx, dt1 = dt * (float)g.ny;
+    const float xmax = (float)g.nx + 0.5f, ymax = (float)g.ny + 0.5f;
+    if (degenerate(g)) {
+        for (int f = 0; f < nf; ++f) {
+            // interior loops are empty: only the trailing set_bnd (lib.rs:125) acts
+            LAUNCH("k_serial_set_bnd", st, k_serial_set_bnd<<<1, 1, 0, st>>>(d[f], g, b[f]));
+        }
+        return 0;
+    }
+    AdvectArgs a{};
+    for (int f = 0; f < nf; ++f) { a.d[f] = d[f]; a.d0[f] = d0[f]; a.b[f] = b[f]; }
+    if (nf == 2)
+        LAUNCH("k_advect2", st, k_advect<2><<<cell_grid(g.nx, g.ny), cell_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax));
+    else
+        LAUNCH("k_advect1", st, k_advect<1><<<cell_grid(g.nx, g.ny), cell_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax));
+    return 0;
+}
+
+// project, src/lib.rs:146-169.
+static int op_project(float* u, float* v, float*& p, float* div, float*& scratch, const Geom& g, int iters, int fused,
+                      cudaStream_t st) {
+    if (degenerate(g)) {
+        LAUNCH("k_serial_project", st, k_serial_project<<<1, 1, 0, st>>>(u, v, p, div, scratch, g, iters));
+        return 0;
+    }
+    const float sx = -0.5f / (float)g.nx, sy = -0.5f / (float)g.ny;  // lib.rs:156-157
+    LAUNCH("k_divergence", st, k_divergence<<<cell_grid(g.nx, g.ny), cell_block(), 0, st>>>(div, p, u, v, g, sx, sy));
+    TRY(op_lin_solve(B_POSITIVE, p, div, scratch, g, 1.0f, 4.0f, iters, fused, st));  // lib.rs:162
+    const float gx = -0.5f * (float)g.nx, gy = -0.5f * (float)g.ny;  // lib.rs:164-165
+    LAUNCH("k_gradient", st, k_gradient<<<cell_grid(g.nx, g.ny), cell_block(), 0, st>>>(u, v, p, g, gx, gy));
+    return 0;
+}
+
+// vel_step, src/lib.rs:181-208 (argument roles alternate exactly as in the reference;
+// no SWAPs -- lib.rs:193,196,201-202 are commented out there).
+static int op_vel_step(float*& u, float*& v, float*& u0, float*& v0, float*& s, const Geom& g, float visc, float dt,
+                       int iters, int fused, cudaStream_t st) {
+    TRY(op_add_source(u, u0, v, v0, g, dt, st));                            // lib.rs:190-191
+    TRY(op_diffuse(B_NEGX, u0, u, s, g, visc, dt, iters, fused, st));       // lib.rs:194
+    TRY(op_diffuse(B_NEGY, v0, v, s, g, visc, dt, iters, fused, st));       // lib.rs:197
+    TRY(op_project(u0, v0, u, v, s, g, iters, fused, st));                  // lib.rs:199
+    float* d[2] = {u, v};
+    const float* d0[2] = {u0, v0};
+    const int b[2] = {B_NEGX, B_NEGY};
+    TRY(op_advect(2, d, d0, b, u0, v0, g, dt, st));                         // lib.rs:204-205
+    return op_project(u, v, u0, v0, s, g, iters, fused, st);                // lib.rs:207
+}
+
+// dens_step, src/lib.rs:171-179.
+static int op_dens_step(float*& x, float*& x0, const float* u, const float* v, float*& s, const Geom& g, float diff,
+                        float dt, int iters, int fused, cudaStream_t st) {
+    TRY(op_add_source(x, x0, nullptr, nullptr, g, dt, st));                 // lib.rs:172
+    TRY(op_diffuse(B_POSITIVE, x0, x, s, g, diff, dt, iters, fused, st));   // lib.rs:175
+    float* d[1] = {x};
+    const float* d0[1] = {x0};
+    const int b[1] = {B_POSITIVE};
+    return op_advect(1, d, d0, b, u, v, g, dt, st);                         // lib.rs:178
+}
+
+// --------------------------------------------------------------------------------------
+// handles
+// --------------------------------------------------------------------------------------
+struct FieldSet {
+    Geom g{};
+    int n = 0;
+    float* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev = nullptr;
+    int iters = 20;  // src/lib.rs:52
+    int fused = 0;   // 0 = library default
+    int device = 0;
+
+    int init(size_t w, size_t h, int nfields) {
+        if (w < 2 || h < 2) return fail(FRUID_ERR_BAD_SIZE, "grid must be at least 2x2 (got %zux%zu)", w, h);
+        if (w > (size_t)1 << 20 || h > (size_t)1 << 20) return fail(FRUID_ERR_BAD_SIZE, "grid too large (%zux%zu)", w, h);
+        CU(cudaGetDevice(&device));
+        g = make_geom(w, h, pitch_for(w));
+        n = nfields;
+        CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        const size_t bytes = g.pitch * h * sizeof(float);
+        for (int i = 0; i < n; ++i) {
+            CU(cudaMalloc(&buf[i], bytes));
+            CU(cudaMemsetAsync(buf[i], 0, bytes, stream));  // Array2D::new zero-fills, lib.rs:218,257
+        }
+        return 0;
+    }
+    void release() {
+        if (stream) cudaStreamSynchronize(stream);
+        for (int i = 0; i < 5; ++i) if (buf[i]) cudaFree(buf[i]);
+        if (ev) cudaEventDestroy(ev);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    int upload(int field, const float* host) {
+        if (field < 0 || field >= n - 1 || !host) return fail(FRUID_ERR_BAD_ARG, "bad field %d or null host pointer", field);
+        CU(cudaMemcpy2DAsync(buf[field], g.pitch * sizeof(float), host, (size_t)g.w * sizeof(float),
+                             (size_t)g.w * sizeof(float), (size_t)g.h, cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));  // host buffer may be pageable and reused by the caller
+        return 0;
+    }
+    int download(int field, float* host) {
+        if (field < 0 || field >= n || !host) return fail(FRUID_ERR_BAD_ARG, "bad field %d or null host pointer", field);
+        CU(cudaMemcpy2DAsync(host, (size_t)g.w * sizeof(float), buf[field], g.pitch * sizeof(float),
+                             (size_t)g.w * sizeof(float), (size_t)g.h, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        return 0;
+    }
+    int inject(int field, size_t x, size_t y, float val) {
+        if (field < 0 || field >= n - 1) return fail(FRUID_ERR_BAD_ARG, "bad field %d", field);
+        if (x >= (size_t)g.w || y >= (size_t)g.h) return fail(FRUID_ERR_BAD_ARG, "cell (%zu,%zu) outside %dx%d", x, y, g.w, g.h);
+        CU(cudaMemcpyAsync(buf[field] + x + y * g.pitch, &val, sizeof(float), cudaMemcpyHostToDevice, stream));
+        return 0;
+    }
+    int set_iters(int k) {
+        if (k < 2 || (k & 1)) return fail(FRUID_ERR_ODD_ITERATIONS, "iterations must be even and >= 2, got %d", k);
+        iters = k;
+        return 0;
+    }
+    int set_fused(int t) {
+        if (t < 0 || (t > 1 && (t & 1))) return fail(FRUID_ERR_BAD_ARG, "fused sweeps must be 0 (default), 1 or even, got %d", t);
+        fused = t;
+        return 0;
+    }
+};
+
+struct fruid_fluid { FieldSet s; };    // buf: 0=u 1=v 2=u_prev 3=v_prev 4=scratch (lib.rs:247-253)
+struct fruid_density { FieldSet s; };  // buf: 0=dens 1=dens_prev 2=scratch        (lib.rs:210-214)
+
+#define NEED(h) do { if (!(h)) return fail(FRUID_ERR_BAD_ARG, "null handle"); CU(cudaSetDevice((h)->s.device)); } while (0)
+
+extern "C" int fruid_fluid_create(size_t w, size_t h, fruid_fluid_t** out) {
+    if (!out) return fail(FRUID_ERR_BAD_ARG, "null out pointer");
+    *out = nullptr;
+    fruid_fluid* f = new (std::nothrow) fruid_fluid();
+    if (!f) return fail(FRUID_ERR_OOM, "host allocation failed");
+    int r = f->s.init(w, h, 5);
+    if (r) { f->s.release(); delete f; return r; }
+    *out = f;
+    return 0;
+}
+extern "C" int fruid_fluid_destroy(fruid_fluid_t* f) {
+    if (!f) return 0;
+    cudaSetDevice(f->s.device);
+    f->s.release();
+    delete f;
+    return 0;
+}
+extern "C" size_t fruid_fluid_width(const fruid_fluid_t* f) { return f ? (size_t)f->s.g.w : 0; }
+extern "C" size_t fruid_fluid_height(const fruid_fluid_t* f) { return f ? (size_t)f->s.g.h : 0; }
+extern "C" int fruid_fluid_upload(fruid_fluid_t* f, int field, const float* host) { NEED(f); return f->s.upload(field, host); }
+extern "C" int fruid_fluid_download(fruid_fluid_t* f, int field, float* host) {
+    NEED(f);
+    if (field == 4) return fail(FRUID_ERR_BAD_ARG, "scratch is not observable (lib.rs:252)");
+    return f->s.download(field, host);
+}
+extern "C" int fruid_fluid_inject(fruid_fluid_t* f, int field, size_t x, size_t y, float val) { NEED(f); return f->s.inject(field, x, y, val); }
+extern "C" int fruid_fluid_set_iterations(fruid_fluid_t* f, int k) { NEED(f); return f->s.set_iters(k); }
+extern "C" int fruid_fluid_set_fused_sweeps(fruid_fluid_t* f, int t) { NEED(f); return f->s.set_fused(t); }
+extern "C" int fruid_fluid_step(fruid_fluid_t* f, float dt, float visc) {
+    NEED(f);
+    FieldSet& s = f->s;
+    return op_vel_step(s.buf[0], s.buf[1], s.buf[2], s.buf[3], s.buf[4], s.g, visc, dt, s.iters, s.fused, s.stream);
+}
+extern "C" int fruid_fluid_step_n(fruid_fluid_t* f, float dt, float visc, int n) {
+    NEED(f);
+    if (n < 0) return fail(FRUID_ERR_BAD_ARG, "negative step count");
+    for (int i = 0; i < n; ++i) TRY(fruid_fluid_step(f, dt, visc));
+    return 0;
+}
+extern "C" void* fruid_fluid_stream(fruid_fluid_t* f) { return f ? (void*)f->s.stream : nullptr; }
+extern "C" int fruid_fluid_sync(fruid_fluid_t* f) { NEED(f); CU(cudaStreamSynchronize(f->s.stream)); CU(cudaGetLastError()); return 0; }
+
+extern "C" int fruid_density_create(size_t w, size_t h, fruid_density_t** out) {
+    if (!out) return fail(FRUID_ERR_BAD_ARG, "null out pointer");
+    *out = nullptr;
+    fruid_density* d = new (std::nothrow) fruid_density();
+    if (!d) return fail(FRUID_ERR_OOM, "host allocation failed");
+    int r = d->s.init(w, h, 3);
+    if (r) { d->s.release(); delete d; return r; }
+    *out = d;
+    return 0;
+}
+extern "C" int fruid_density_destroy(fruid_density_t* d) {
+    if (!d) return 0;
+    cudaSetDevice(d->s.device);
+    d->s.release();
+    delete d;
+    return 0;
+}
+extern "C" int fruid_density_upload(fruid_density_t* d, int field, const float* host) { NEED(d); return d->s.upload(field, host); }
+extern "C" int fruid_density_download(fruid_density_t* d, int field, float* host) {
+    NEED(d);
+    if (field == 2) return fail(FRUID_ERR_BAD_ARG, "scratch is not observable (lib.rs:213)");
+    return d->s.download(field, host);
+}
+extern "C" int fruid_density_inject(fruid_density_t* d, int field, size_t x, size_t y, float val) { NEED(d); return d->s.inject(field, x, y, val); }
+extern "C" int fruid_density_fill(fruid_density_t* d, int field, float val) {
+    NEED(d);
+    FieldSet& s = d->s;
+    if (field < 0 || field > 1) return fail(FRUID_ERR_BAD_ARG, "bad field %d", field);
+    if (val == 0.0f && !std::signbit(val)) {
+        CU(cudaMemsetAsync(s.buf[field], 0, s.g.pitch * (size_t)s.g.h * sizeof(float), s.stream));
+        return 0;
+    }
+    LAUNCH("k_fill", s.stream, k_fill<<<cell_grid(s.g.w, s.g.h), cell_block(), 0, s.stream>>>(s.buf[field], s.g, val));
+    return 0;
+}
+extern "C" int fruid_density_set_iterations(fruid_density_t* d, int k) { NEED(d); return d->s.set_iters(k); }
+extern "C" int fruid_density_set_fused_sweeps(fruid_density_t* d, int t) { NEED(d); return d->s.set_fused(t); }
+extern "C" int fruid_density_step_dev(fruid_density_t* d, fruid_fluid_t* vel, float dt, float diff) {
+    NEED(d);
+    if (!vel) return fail(FRUID_ERR_BAD_ARG, "null velocity handle");
+    FieldSet& s = d->s;
+    FieldSet& vs = vel->s;
+    if (vs.g.w != s.g.w || vs.g.h != s.g.h)
+        return fail(FRUID_ERR_SIZE_MISMATCH, "density %dx%d vs velocity %dx%d", s.g.w, s.g.h, vs.g.w, vs.g.h);
+    if (vs.device != s.device) return fail(FRUID_ERR_BAD_ARG, "density and velocity live on different devices");
+    // u,v are produced on vel's stream and consumed on ours; order both ways.
+    CU(cudaEventRecord(vs.ev, vs.stream));
+    CU(cudaStreamWaitEvent(s.stream, vs.ev, 0));
+    TRY(op_dens_step(s.buf[0], s.buf[1], vs.buf[0], vs.buf[1], s.buf[2], s.g, diff, dt, s.iters, s.fused, s.stream));
+    CU(cudaEventRecord(s.ev, s.stream));
+    CU(cudaStreamWaitEvent(vs.stream, s.ev, 0));
+    return 0;
+}
+extern "C" int fruid_density_step_host(fruid_density_t* d, const float* u, const float* v, float dt, float diff) {
+    NEED(d);
+    if (!u || !v) return fail(FRUID_ERR_BAD_ARG, "null velocity pointer");
+    FieldSet& s = d->s;
+    const size_t bytes = s.g.pitch * (size_t)s.g.h * sizeof(float);
+    float *du = nullptr, *dv = nullptr;
+    CU(cudaMallocAsync(&du, bytes, s.stream));
+    CU(cudaMallocAsync(&dv, bytes, s.stream));
+    const size_t rb = (size_t)s.g.w * sizeof(float);
+    CU(cudaMemcpy2DAsync(du, s.g.pitch * sizeof(float), u, rb, rb, (size_t)s.g.h, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemcpy2DAsync(dv, s.g.pitch * sizeof(float), v, rb, rb, (size_t)s.g.h, cudaMemcpyHostToDevice, s.stream));
+    int r = op_dens_step(s.buf[0], s.buf[1], du, dv, s.buf[2], s.g, diff, dt, s.iters, s.fused, s.stream);
+    cudaFreeAsync(du, s.stream);
+    cudaFreeAsync(dv, s.stream);
+    TRY(r);
+    CU(cudaStreamSynchronize(s.stream));
+    return 0;
+}
+extern "C" void* fruid_density_stream(fruid_density_t* d) { return d ? (void*)d->s.stream : nullptr; }
+extern "C" int fruid_density_sync(fruid_density_t* d) { NEED(d); CU(cudaStreamSynchronize(d->s.stream)); CU(cudaGetLastError()); return 0; }
+
+// Page-lock caller-owned host arrays (the Vec<f32> inside an Array2D has a fixed length for
+// the object's life) so uploads/downloads run at full PCIe rate.
+extern "C" int fruid_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return fail(FRUID_ERR_BAD_ARG, "null pointer or zero size");
+    CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    return 0;
+}
+extern "C" int fruid_host_unregister(void* p) {
+    if (!p) return fail(FRUID_ERR_BAD_ARG, "null pointer");
+    CU(cudaHostUnregister(p));
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------
+// per-operator entry points on host arrays
+// --------------------------------------------------------------------------------------
+namespace {
+struct Scratch {  // a few temporary device fields for one operator call
+    Geom g{};
+    std::vector<float*> bufs;
+    ~Scratch() { for (float* p : bufs) cudaFree(p); }
+    int init(size_t w, size_t h) {
+        if (w < 2 || h < 2) return fail(FRUID_ERR_BAD_SIZE, "grid must be at least 2x2 (got %zux%zu)", w, h);
+        g = make_geom(w, h, pitch_for(w));
+        return 0;
+    }
+    int put(const float* host, float** out) {
+        float* d = nullptr;
+        const size_t bytes = g.pitch * (size_t)g.h * sizeof(float);
+        CU(cudaMalloc(&d, bytes));
+        bufs.push_back(d);
+        CU(cudaMemset(d, 0, bytes));
+        if (host) CU(cudaMemcpy2D(d, g.pitch * sizeof(float), host, (size_t)g.w * sizeof(float), (size_t)g.w * sizeof(float),
+                                  (size_t)g.h, cudaMemcpyHostToDevice));
+        *out = d;
+        return 0;
+    }
+    int get(float* host, const float* d) {
+        CU(cudaDeviceSynchronize());
+        CU(cudaMemcpy2D(host, (size_t)g.w * sizeof(float), d, g.pitch * sizeof(float), (size_t)g.w * sizeof(float), (size_t)g.h,
+                        cudaMemcpyDeviceToHost));
+        return 0;
+    }
+};
+}  // namespace
+
+extern "C" int fruid_op_add_source(float* x, const float* s, size_t w, size_t h, float dt) {
+    if (!x || !s) return fail(FRUID_ERR_BAD_ARG, "null pointer");
+    Scratch sc; TRY(sc.init(w, h));
+    float *dx = nullptr, *ds = nullptr;
+    TRY(sc.put(x, &dx)); TRY(sc.put(s, &ds));
+    TRY(op_add_source(dx, ds, nullptr, nullptr, sc.g, dt, 0));
+    return sc.get(x, dx);
+}
+extern "C" int fruid_op_set_bnd(int b, float* x, size_t w, size_t h) {
+    if (!x || b < 0 || b > 2) return fail(FRUID_ERR_BAD_ARG, "null pointer or bad bounds kind");
+    Scratch sc; TRY(sc.init(w, h));
+    float* dx = nullptr;
+    TRY(sc.put(x, &dx));
+    TRY(op_set_bnd(b, dx, sc.g, 0));
+    return sc.get(x, dx);
+}
+extern "C" int fruid_op_lin_solve(int b, float* x, const float* x0, float* scratch, size_t w, size_t h, float a, float c,
+                                  int iters, int fused) {
+    if (!x || !x0 || !scratch || b < 0 || b > 2) return fail(FRUID_ERR_BAD_ARG, "null pointer or bad bounds kind");
+    Scratch sc; TRY(sc.init(w, h));
+    float *dx = nullptr, *dx0 = nullptr, *ds = nullptr;
+    TRY(sc.put(x, &dx)); TRY(sc.put(x0, &dx0)); TRY(sc.put(scratch, &ds));
+    TRY(op_lin_solve(b, dx, dx0, ds, sc.g, a, c, iters, fused, 0));
+    TRY(sc.get(x, dx));
+    return sc.get(scratch, ds);
+}
+extern "C" int fruid_op_diffuse(int b, float* x, const float* x0, float* scratch, size_t w, size_t h, float diff, float dt,
+                                int iters, int fused) {
+    if (!x || !x0 || !scratch || b < 0 || b > 2) return fail(FRUID_ERR_BAD_ARG, "null pointer or bad bounds kind");
+    Scratch sc; TRY(sc.init(w, h));
+    float *dx = nullptr, *dx0 = nullptr, *ds = nullptr;
+    TRY(sc.put(x, &dx)); TRY(sc.put(x0, &dx0)); TRY(sc.put(scratch, &ds));
+    TRY(op_diffuse(b, dx, dx0, ds, sc.g, diff, dt, iters, fused, 0));
+    TRY(sc.get(x, dx));
+    return sc.get(scratch, ds);
+}
+extern "C" int fruid_op_advect(int b, float* d, const float* d0, const float* u, const float* v, size_t w, size_t h,
+                               float dt) {
+    if (!d || !d0 || !u || !v || b < 0 || b > 2) return fail(FRUID_ERR_BAD_ARG, "null pointer or bad bounds kind");
+    if (d == d0 || d == u || d == v) return fail(FRUID_ERR_BAD_ARG, "advect output must not alias an input (lib.rs:84)");
+    Scratch sc; TRY(sc.init(w, h));
+    float *dd = nullptr, *dd0 = nullptr, *du = nullptr, *dv = nullptr;
+    TRY(sc.put(d, &dd));
+    TRY(sc.put(d0, &dd0));
+    if (u == d0) du = dd0; else TRY(sc.put(u, &du));
+    if (v == d0) dv = dd0; else if (v == u) dv = du; else TRY(sc.put(v, &dv));
+    float* dl[1] = {dd};
+    const float* d0l[1] = {dd0};
+    const int bl[1] = {b};
+    TRY(op_advect(1, dl, d0l, bl, du, dv, sc.g, dt, 0));
+    return sc.get(d, dd);
+}
+extern "C" int fruid_op_project(float* u, float* v, float* p, float* div, float* scratch, size_t w, size_t h, int iters,
+                                int fused) {
+    if (!u || !v || !p || !div || !scratch) return fail(FRUID_ERR_BAD_ARG, "null pointer");
+    Scratch sc; TRY(sc.init(w, h));
+    float *du = nullptr, *dv = nullptr, *dp = nullptr, *dd = nullptr, *ds = nullptr;
+    TRY(sc.put(u, &du)); TRY(sc.put(v, &dv)); TRY(sc.put(p, &dp)); TRY(sc.put(div, &dd)); TRY(sc.put(scratch, &ds));
+    TRY(op_project(du, dv, dp, dd, ds, sc.g, iters, fused, 0));
+    TRY(sc.get(u, du)); TRY(sc.get(v, dv)); TRY(sc.get(p, dp)); TRY(sc.get(div, dd));
+    return sc.get(scratch, ds);
+}
+
+// --------------------------------------------------------------------------------------
+// device-pointer variants
+// --------------------------------------------------------------------------------------
+static int check_dev_layout(const void* p, size_t w, size_t h, size_t pitch) {
+    if (w < 2 || h < 2) return fail(FRUID_ERR_BAD_SIZE, "grid must be at least 2x2");
+    if (pitch < w || (pitch & 3) || ((uintptr_t)p & 15)) return fail(FRUID_ERR_BAD_ARG, "pitch must be >= w and a multiple of 4 floats; base 16-byte aligned");
+    return 0;
+}
+extern "C" int fruid_dev_lin_solve(int b, float* x, const float* x0, float* scratch, size_t w, size_t h, size_t pitch, float a,
+                                   float c, int iters, int fused, void* stream) {
+    TRY(check_dev_layout(x, w, h, pitch)); TRY(check_dev_layout(x0, w, h, pitch)); TRY(check_dev_layout(scratch, w, h, pitch));
+    float* const x_in = x;
+    TRY(op_lin_solve(b, x, x0, scratch, make_geom(w, h, pitch), a, c, iters, fused, (cudaStream_t)stream));
+    if (x != x_in)  // odd number of launches: the newest iterate sits in the caller's scratch
+        CU(cudaMemcpyAsync(x_in, x, pitch * h * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int fruid_dev_advect(int b, float* d, const float* d0, const float* u, const float* v, size_t w, size_t h,
+                                size_t pitch, float dt, void* stream) {
+    TRY(check_dev_layout(d, w, h, pitch)); TRY(check_dev_layout(d0, w, h, pitch));
+    float* dl[1] = {d};
+    const float* d0l[1] = {d0};
+    const int bl[1] = {b};
+    return op_advect(1, dl, d0l, bl, u, v, make_geom(w, h, pitch), dt, (cudaStream_t)stream);
+}

@@ -1,0 +1,152 @@
+/*
+ * fruid_b200.h -- C ABI of the B200-native stable-fluids time step.
+ *
+ * Drop-in boundary for Masterchef365/fruid's solver (reference src/lib.rs).
+ * The reference has NO pre-existing FFI: its boundary is the Rust crate API
+ *     pub type Array2D            src/lib.rs:1
+ *     DensitySim::{new,step,density,density_mut}      src/lib.rs:216-245
+ *     FluidSim::{new,step,uv,uv_mut,width,height}     src/lib.rs:255-294
+ * This header is what a Rust shim keeping those signatures binds with
+ * `extern "C"` (INTEGRATION.md shows the shim); include/fruid.hpp is the same
+ * mirror in C++ and fruid_b200/api.py in Python (ctypes).
+ *
+ * Conventions
+ *   - Fields are f32, w x h cells INCLUDING the 1-cell border (the constructor
+ *     arguments of FluidSim::new / DensitySim::new).  Host arrays are dense,
+ *     index (x, y) -> x + y*w (idek_basics::Array2D layout).
+ *   - Every function returns 0 (FRUID_OK) or a negative fruid_status;
+ *     fruid_last_error() gives a thread-local message for the last failure.
+ *     The reference API is infallible (misuse panics); a shim panics on != 0.
+ *   - A handle is not thread-safe; distinct handles may be used from distinct
+ *     threads.  Work is enqueued on the handle's CUDA stream; download/sync
+ *     calls block until the data is on the host.
+ *   - There is no CPU fallback: without a CUDA device every call fails with
+ *     FRUID_ERR_CUDA.
+ */
+#ifndef FRUID_B200_H
+#define FRUID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fruid_fluid fruid_fluid_t;     /* device twin of FluidSim   (src/lib.rs:247-253) */
+typedef struct fruid_density fruid_density_t; /* device twin of DensitySim (src/lib.rs:210-214) */
+
+typedef enum fruid_status {
+    FRUID_OK = 0,
+    FRUID_ERR_BAD_SIZE = -1,       /* w < 2 or h < 2 (debug_assert at src/lib.rs:13-14) */
+    FRUID_ERR_SIZE_MISMATCH = -2,  /* density vs velocity size (unchecked at src/lib.rs:226) */
+    FRUID_ERR_ODD_ITERATIONS = -3, /* sweeps per lin_solve must be even and >= 2 */
+    FRUID_ERR_CUDA = -4,
+    FRUID_ERR_NO_PEER = -5,
+    FRUID_ERR_OOM = -6,
+    FRUID_ERR_BAD_ARG = -7
+} fruid_status;
+
+/* enum Bounds, src/lib.rs:19-25 (#[repr(i32)], same values). */
+typedef enum fruid_bounds { FRUID_POSITIVE = 0, FRUID_NEGX = 1, FRUID_NEGY = 2 } fruid_bounds;
+
+/* FluidSim fields, src/lib.rs:247-253.  uv() -> (U, V); uv_mut() -> (U_PREV, V_PREV).
+ * After a step U_PREV holds the pressure and V_PREV the divergence of the
+ * second projection (src/lib.rs:207 -> 146), exactly as in the reference. */
+typedef enum fruid_fluid_field {
+    FRUID_U = 0, FRUID_V = 1, FRUID_U_PREV = 2, FRUID_V_PREV = 3
+} fruid_fluid_field;
+
+/* DensitySim fields, src/lib.rs:210-214.  density() -> DENS; density_mut() -> DENS_PREV. */
+typedef enum fruid_density_field { FRUID_DENS = 0, FRUID_DENS_PREV = 1 } fruid_density_field;
+
+const char *fruid_last_error(void);
+/* Number of kernels this library has launched in this process (all handles). */
+uint64_t fruid_kernel_launch_count(void);
+/* "sm_100a" build tag + version string. */
+const char *fruid_build_info(void);
+
+/* Page-lock / unlock a caller-owned host array (e.g. the Vec<f32> inside an Array2D). */
+int fruid_host_register(void *p, size_t bytes);
+int fruid_host_unregister(void *p);
+
+/* Optional per-kernel timing: when enabled every kernel launch is bracketed by CUDA events
+ * on its stream; fruid_profile_report() synchronises the device, sums durations by kernel
+ * name into out[0..*n) and resets the log. */
+typedef struct fruid_kernel_stat { char name[48]; uint64_t launches; double total_ms; } fruid_kernel_stat;
+int fruid_profile_enable(int on);
+int fruid_profile_report(fruid_kernel_stat *out, size_t cap, size_t *n);
+
+/* ---- FluidSim (src/lib.rs:255-294) ------------------------------------- */
+/* FluidSim::new(width, height), src/lib.rs:256: five zeroed w x h fields. */
+int fruid_fluid_create(size_t w, size_t h, fruid_fluid_t **out);
+int fruid_fluid_destroy(fruid_fluid_t *f);
+/* FluidSim::width / height, src/lib.rs:287-293. */
+size_t fruid_fluid_width(const fruid_fluid_t *f);
+size_t fruid_fluid_height(const fruid_fluid_t *f);
+/* Host <-> device copies of one field (dense w*h floats). */
+int fruid_fluid_upload(fruid_fluid_t *f, int field, const float *host);
+int fruid_fluid_download(fruid_fluid_t *f, int field, float *host);
+/* `u[pos] = val` through uv_mut(), src/main.rs:98-102, without a full upload. */
+int fruid_fluid_inject(fruid_fluid_t *f, int field, size_t x, size_t y, float val);
+/* Sweeps per lin_solve; the reference hard-codes 20 (src/lib.rs:52).  Even only. */
+int fruid_fluid_set_iterations(fruid_fluid_t *f, int k);
+/* Jacobi sweeps fused per kernel launch (0 = library default; 1 = one sweep per launch). */
+int fruid_fluid_set_fused_sweeps(fruid_fluid_t *f, int t);
+/* FluidSim::step(dt, visc), src/lib.rs:267-277 -> vel_step src/lib.rs:181-208.  Asynchronous. */
+int fruid_fluid_step(fruid_fluid_t *f, float dt, float visc);
+/* n identical steps back to back (no host round trip). */
+int fruid_fluid_step_n(fruid_fluid_t *f, float dt, float visc, int n);
+int fruid_fluid_sync(fruid_fluid_t *f);
+/* The handle's cudaStream_t (for event timing / interop). */
+void *fruid_fluid_stream(fruid_fluid_t *f);
+
+/* ---- DensitySim (src/lib.rs:216-245) ------------------------------------ */
+int fruid_density_create(size_t w, size_t h, fruid_density_t **out);
+int fruid_density_destroy(fruid_density_t *d);
+int fruid_density_upload(fruid_density_t *d, int field, const float *host);
+int fruid_density_download(fruid_density_t *d, int field, float *host);
+int fruid_density_inject(fruid_density_t *d, int field, size_t x, size_t y, float val);
+/* `density_mut().data_mut().fill(v)`, src/main.rs:105-108. */
+int fruid_density_fill(fruid_density_t *d, int field, float val);
+int fruid_density_set_iterations(fruid_density_t *d, int k);
+int fruid_density_set_fused_sweeps(fruid_density_t *d, int t);
+/* DensitySim::step((u, v), dt, diff), src/lib.rs:226-236 -> dens_step src/lib.rs:171-179,
+ * with (u, v) = vel's device-resident uv() (the `c.step(sim.uv(), ..)` pattern, src/main.rs:115). */
+int fruid_density_step_dev(fruid_density_t *d, fruid_fluid_t *vel, float dt, float diff);
+/* Same, with (u, v) given as host arrays (uploaded first). */
+int fruid_density_step_host(fruid_density_t *d, const float *u, const float *v, float dt, float diff);
+int fruid_density_sync(fruid_density_t *d);
+void *fruid_density_stream(fruid_density_t *d);
+
+/* ---- Per-operator entry points (parity tests / profiling) ---------------
+ * Host arrays in, host arrays out; each call uploads, runs the same kernels the
+ * step uses, and downloads.  `fused` = Jacobi sweeps per launch (0 = default).
+ * They restate the private fns of src/lib.rs: add_source :5, set_bnd :27,
+ * lin_solve :46, diffuse :73, advect :84, project :146, dens_step :171,
+ * vel_step :181. */
+int fruid_op_add_source(float *x, const float *s, size_t w, size_t h, float dt);
+int fruid_op_set_bnd(int b, float *x, size_t w, size_t h);
+/* On return x holds the newest iterate and scratch the previous one (iters even). */
+int fruid_op_lin_solve(int b, float *x, const float *x0, float *scratch, size_t w, size_t h, float a,
+                       float c, int iters, int fused);
+int fruid_op_diffuse(int b, float *x, const float *x0, float *scratch, size_t w, size_t h,
+                     float diff, float dt, int iters, int fused);
+/* d0 may alias u or v (src/lib.rs:204-205); d must be distinct. */
+int fruid_op_advect(int b, float *d, const float *d0, const float *u, const float *v, size_t w,
+                    size_t h, float dt);
+int fruid_op_project(float *u, float *v, float *p, float *div, float *scratch, size_t w, size_t h,
+                     int iters, int fused);
+
+/* ---- Device-pointer variants (buffers already in HBM; used by bench/ncu) --
+ * All pointers are device pointers to rows of `pitch` floats (pitch >= w,
+ * pitch % 4 == 0, base 16-byte aligned); stream is a cudaStream_t (0 = default). */
+int fruid_dev_lin_solve(int b, float *x, const float *x0, float *scratch, size_t w, size_t h,
+                        size_t pitch, float a, float c, int iters, int fused, void *stream);
+int fruid_dev_advect(int b, float *d, const float *d0, const float *u, const float *v, size_t w,
+                     size_t h, size_t pitch, float dt, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRUID_B200_H */

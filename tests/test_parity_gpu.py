@@ -1,0 +1,301 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes), against the
+CPU oracle on the same seeded inputs.  The bar is BIT-EXACT float32 (north-star bound:
+max-relative 1e-5; we assert 0 mismatching cells, NaN == NaN)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_bits, rand_field
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+POS, NEGX, NEGY = 0, 1, 2
+# tiny, non-square, not a multiple of any tile (250 = reference default, src/main.rs:36),
+# and sizes straddling the 128-wide register tile / 32-float pitch padding
+SIZES = [(3, 3), (3, 9), (9, 3), (4, 5), (33, 31), (64, 64), (129, 67), (250, 250), (257, 130), (512, 96)]
+FUSED = [1, 0]  # one sweep per launch, and the library default (fused register-tile kernel)
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import __graft_entry__
+    __graft_entry__.build()
+    import fruid_b200
+    return fruid_b200
+
+
+@pytest.fixture(scope="module")
+def O(oracle_mod):
+    return oracle_mod.lib(True)
+
+
+@pytest.mark.parametrize("w,h", SIZES)
+def test_add_source(fb, O, w, h):
+    rng = np.random.default_rng(1)
+    x, s = rand_field(rng, w, h), rand_field(rng, w, h)
+    xo = x.copy()
+    fb.ops.add_source(x, s, 0.37)
+    O.fruid_oracle_add_source(xo, s, w, h, 0.37)
+    assert_bits(x, xo)
+
+
+@pytest.mark.parametrize("w,h", SIZES + [(2, 2), (2, 7), (7, 2)])
+@pytest.mark.parametrize("b", [POS, NEGX, NEGY])
+def test_set_bnd(fb, O, w, h, b):
+    rng = np.random.default_rng(2)
+    x = rand_field(rng, w, h)
+    xo = x.copy()
+    fb.ops.set_bnd(b, x)
+    O.fruid_oracle_set_bnd(b, xo, w, h)
+    assert_bits(x, xo)
+
+
+@pytest.mark.parametrize("w,h", SIZES + [(2, 2), (2, 7), (7, 2)])
+@pytest.mark.parametrize("b", [POS, NEGX, NEGY])
+@pytest.mark.parametrize("fused", FUSED)
+@pytest.mark.parametrize("a,c", [(1.0, 4.0), (0.0, 1.0), (0.731, 3.924)])
+def test_lin_solve(fb, O, w, h, b, fused, a, c):
+    rng = np.random.default_rng(3)
+    x, x0, s = rand_field(rng, w, h), rand_field(rng, w, h), rand_field(rng, w, h)
+    xo, so = x.copy(), s.copy()
+    fb.ops.lin_solve(b, x, x0, s, a, c, 20, fused)
+    O.fruid_oracle_lin_solve(b, xo, x0, so, w, h, a, c, 20, 1)
+    assert_bits(x, xo, "x")
+
+
+@pytest.mark.parametrize("iters", [2, 4, 6, 20, 26, 40, 100])
+@pytest.mark.parametrize("fused", [0, 2, 4, 6, 10, 20])
+def test_lin_solve_iteration_counts(fb, O, iters, fused):
+    w, h = 300, 270
+    rng = np.random.default_rng(4)
+    x, x0, s = rand_field(rng, w, h), rand_field(rng, w, h), rand_field(rng, w, h)
+    xo, so = x.copy(), s.copy()
+    fb.ops.lin_solve(NEGY, x, x0, s, 0.4, 2.6, iters, fused)
+    O.fruid_oracle_lin_solve(NEGY, xo, x0, so, w, h, 0.4, 2.6, iters, 1)
+    assert_bits(x, xo, "x")
+
+
+def test_odd_iterations_are_rejected(fb):
+    x = np.zeros((8, 8), np.float32)
+    with pytest.raises(fb.FruidError) as e:
+        fb.ops.lin_solve(0, x, x.copy(), x.copy(), 1.0, 4.0, 19, 0)
+    assert e.value.code == fb._lib.ERR_ODD_ITERATIONS
+
+
+@pytest.mark.parametrize("w,h", SIZES)
+@pytest.mark.parametrize("diff", [0.0, 1e-5, 2e-3])
+def test_diffuse(fb, O, w, h, diff):
+    rng = np.random.default_rng(5)
+    x, x0, s = rand_field(rng, w, h), rand_field(rng, w, h), rand_field(rng, w, h)
+    xo, so = x.copy(), s.copy()
+    fb.ops.diffuse(NEGX, x, x0, s, diff, 0.1, 20, 0)
+    O.fruid_oracle_diffuse(NEGX, xo, x0, so, w, h, diff, 0.1, 20, 1)
+    assert_bits(x, xo)
+
+
+@pytest.mark.parametrize("w,h", SIZES + [(2, 5)])
+@pytest.mark.parametrize("b", [POS, NEGX, NEGY])
+@pytest.mark.parametrize("speed", [0.0, 0.5, 30.0, 4500.0])
+def test_advect(fb, O, w, h, b, speed):
+    rng = np.random.default_rng(6)
+    d0, u, v = rand_field(rng, w, h), rand_field(rng, w, h, speed), rand_field(rng, w, h, speed)
+    d = rand_field(rng, w, h)
+    do = d.copy()
+    fb.ops.advect(b, d, d0, u, v, 0.1)
+    O.fruid_oracle_advect(b, do, d0, u, v, w, h, 0.1, 1)
+    assert_bits(d, do)
+
+
+def test_advect_aliased_like_velocity_self_advection(fb, O):
+    """lib.rs:204: advect(NegX, u, u0, u0, v0, dt) -- d0 aliases u."""
+    w, h = 130, 70
+    rng = np.random.default_rng(7)
+    u0, v0 = rand_field(rng, w, h, 5.0), rand_field(rng, w, h, 5.0)
+    d, do = np.zeros((h, w), np.float32), np.zeros((h, w), np.float32)
+    fb.ops.advect(NEGX, d, u0, u0, v0, 0.1)
+    O.fruid_oracle_advect(NEGX, do, u0, u0, v0, w, h, 0.1, 1)
+    assert_bits(d, do)
+
+
+def test_advect_special_values(fb, O):
+    """NaN passes the clamps and casts to 0 (lib.rs:95-112); +-inf saturate at the clamps;
+    -0.0 and denormals are preserved (no FTZ)."""
+    w, h = 40, 24
+    rng = np.random.default_rng(8)
+    d0, u, v = rand_field(rng, w, h), rand_field(rng, w, h, 2.0), rand_field(rng, w, h, 2.0)
+    u[3, 3], v[4, 4], u[5, 5], v[6, 6] = np.nan, np.inf, -np.inf, np.nan
+    d0[10, 10], d0[11, 11], d0[12, 12] = np.float32(1e-42), -0.0, np.nan
+    u[10, 10] = v[10, 10] = u[11, 11] = v[11, 11] = 0.0
+    d, do = np.zeros((h, w), np.float32), np.zeros((h, w), np.float32)
+    fb.ops.advect(POS, d, d0, u, v, 0.1)
+    O.fruid_oracle_advect(POS, do, d0, u, v, w, h, 0.1, 1)
+    assert_bits(d, do)
+    assert d[10, 10] == np.float32(1e-42)
+
+
+@pytest.mark.parametrize("w,h", SIZES + [(2, 2), (5, 2)])
+@pytest.mark.parametrize("fused", FUSED)
+def test_project(fb, O, w, h, fused):
+    rng = np.random.default_rng(9)
+    u, v, p, div, s = (rand_field(rng, w, h) for _ in range(5))
+    uo, vo, po, divo, so = (a.copy() for a in (u, v, p, div, s))
+    fb.ops.project(u, v, p, div, s, 20, fused)
+    O.fruid_oracle_project(uo, vo, po, divo, so, w, h, 20, 1)
+    for a, b_, n in ((u, uo, "u"), (v, vo, "v"), (p, po, "p"), (div, divo, "div")):
+        assert_bits(a, b_, n)
+
+
+def test_lin_solve_denormals_and_negative_zero(fb, O):
+    w, h = 70, 40
+    rng = np.random.default_rng(10)
+    x = (rand_field(rng, w, h) * 1e-38).astype(np.float32)   # denormal range after scaling
+    x0 = (rand_field(rng, w, h) * 1e-39).astype(np.float32)
+    x0[5, 5] = -0.0
+    s = np.zeros((h, w), np.float32)
+    xo, so = x.copy(), s.copy()
+    fb.ops.lin_solve(POS, x, x0, s, 0.0, 1.0, 20, 0)
+    O.fruid_oracle_lin_solve(POS, xo, x0, so, w, h, 0.0, 1.0, 20, 1)
+    assert_bits(x, xo)
+
+
+# ---- whole steps through the handle API ----------------------------------------------------
+def _load_fluid(fb, sim, fields):
+    for arr, field in zip(fields, (0, 1, 2, 3)):
+        fb._lib.check(fb._lib.lib.fruid_fluid_upload(sim._h, field, fb._lib.ptr(arr)))
+
+
+def _read_fluid(fb, sim, w, h):
+    out = []
+    for field in (0, 1, 2, 3):
+        a = np.empty((h, w), np.float32)
+        fb._lib.check(fb._lib.lib.fruid_fluid_download(sim._h, field, fb._lib.ptr(a)))
+        out.append(a)
+    return out
+
+
+@pytest.mark.parametrize("w,h", [(3, 3), (2, 2), (2, 6), (31, 45), (250, 250), (300, 140)])
+@pytest.mark.parametrize("visc", [0.0, 2e-4])
+@pytest.mark.parametrize("fused", FUSED)
+def test_fluid_steps(fb, oracle_mod, w, h, visc, fused):
+    rng = np.random.default_rng(11)
+    init = [rand_field(rng, w, h) for _ in range(4)]
+    sim = fb.FluidSim(w, h)
+    sim.set_fused_sweeps(fused)
+    _load_fluid(fb, sim, init)
+    of = oracle_mod.Fluid(w, h)
+    for a, src in zip((of.u, of.v, of.u_prev, of.v_prev), init):
+        a[:] = src
+    for step in range(3):
+        sim.step(0.1, visc)
+        of.step(0.1, visc)
+    got = _read_fluid(fb, sim, w, h)
+    for g, want, n in zip(got, (of.u, of.v, of.u_prev, of.v_prev), ("u", "v", "u_prev=p", "v_prev=div")):
+        assert_bits(g, want, n)
+
+
+@pytest.mark.parametrize("name", ["steps_37x29_visc.npz", "steps_30x41_inviscid.npz"])
+def test_golden_steps_on_gpu(fb, name):
+    g = np.load(os.path.join(GOLD, name))
+    w, h = int(g["w"]), int(g["h"])
+    sim, den = fb.FluidSim(w, h), fb.DensitySim(w, h)
+    _load_fluid(fb, sim, [np.ascontiguousarray(g["in_" + k]) for k in ("u", "v", "u_prev", "v_prev")])
+    for k, field in (("dens", 0), ("dens_prev", 1)):
+        fb._lib.check(fb._lib.lib.fruid_density_upload(den._h, field, fb._lib.ptr(np.ascontiguousarray(g["in_" + k]))))
+    for _ in range(int(g["nsteps"])):
+        sim.step(float(g["dt"]), float(g["visc"]))
+        den.step(sim.uv(), float(g["dt"]), float(g["diff"]))
+    got = _read_fluid(fb, sim, w, h)
+    for a, k in zip(got, ("u", "v", "u_prev", "v_prev")):
+        assert_bits(a, g["out_" + k], k)
+    for k, field in (("dens", 0), ("dens_prev", 1)):
+        a = np.empty((h, w), np.float32)
+        fb._lib.check(fb._lib.lib.fruid_density_download(den._h, field, fb._lib.ptr(a)))
+        assert_bits(a, g["out_" + k], k)
+
+
+def _scene_fields(s):
+    u, v = s.sim.uv()
+    p, dv = s.sim.uv_mut()
+    out = {"u": u.numpy(), "v": v.numpy(), "u_prev": p.numpy(), "v_prev": dv.numpy()}
+    for i, d in enumerate(s.dyes):
+        out[f"dens{i}"] = d.density().numpy()
+        out[f"dens_prev{i}"] = d.density_mut().numpy()
+    return out
+
+
+def test_reference_scene_small_vs_golden(fb):
+    from fruid_b200.scene import Scene
+    g = np.load(os.path.join(GOLD, "scene_64x48_f6.npz"))
+    s = Scene(fb.FluidSim, fb.DensitySim, 64, 48)
+    s.run(6)
+    for k, a in _scene_fields(s).items():
+        assert_bits(a, g[k], k)
+
+
+@pytest.mark.parametrize("key,w,h,frames", [("250x250_f100", 250, 250, 100), ("128x128_f100", 128, 128, 100)])
+def test_reference_scene_checksums(fb, key, w, h, frames):
+    """BASELINE.json configs[0]: the default scene (src/main.rs:36: 250x250; plus the 128x128
+    variant), 100 frames, against checksums of the oracle run."""
+    from fruid_b200.scene import Scene
+    sums = json.load(open(os.path.join(GOLD, "scene_checksums.json")))[key]
+    s = Scene(fb.FluidSim, fb.DensitySim, w, h)
+    s.run(frames)
+    for k, a in _scene_fields(s).items():
+        assert hashlib.sha256(a.tobytes()).hexdigest() == sums["sha256"][k], k
+
+
+def test_density_step_with_host_velocity(fb, oracle_mod):
+    w, h = 90, 77
+    rng = np.random.default_rng(12)
+    u, v = rand_field(rng, w, h, 4.0), rand_field(rng, w, h, 4.0)
+    src = rand_field(rng, w, h)
+    den = fb.DensitySim(w, h)
+    od = oracle_mod.Density(w, h)
+    den.density_mut().data_mut()[:] = src.reshape(-1)
+    od.dens_prev[:] = src
+    for _ in range(2):
+        den.step((u, v), 0.1, 1e-4)
+        od.step((u, v), 0.1, 1e-4)
+    assert_bits(den.density().numpy(), od.dens, "dens")
+    assert_bits(den.density_mut().numpy(), od.dens_prev, "dens_prev")
+
+
+def test_api_mirror_semantics(fb):
+    """uv_mut() exposes (u_prev, v_prev); single-cell writes reach the device; size mismatch
+    is an error instead of the reference's out-of-bounds panic (lib.rs:226)."""
+    sim = fb.FluidSim(40, 30)
+    assert (sim.width(), sim.height()) == (40, 30)
+    u0, v0 = sim.uv_mut()
+    u0[(20, 15)] = 100.0
+    assert u0[(20, 15)] == 100.0
+    sim.step(0.1, 0.0)
+    assert sim.uv()[0].numpy().any()
+    assert np.isfinite(sim.uv_mut()[0].numpy()).all()
+    with pytest.raises(IndexError):
+        u0[(40, 0)] = 1.0
+    den = fb.DensitySim(41, 30)
+    with pytest.raises(fb.FruidError) as e:
+        den.step(sim.uv(), 0.1, 0.0)
+    assert e.value.code == fb._lib.ERR_SIZE_MISMATCH
+    with pytest.raises(fb.FruidError) as e:
+        fb.FluidSim(1, 5)
+    assert e.value.code == fb._lib.ERR_BAD_SIZE
+
+
+@pytest.mark.parametrize("w,h", [(1024, 1024)])
+def test_config1_scale_short(fb, oracle_mod, w, h):
+    """BASELINE.json configs[1] (1024x1024 injection scene), shortened to 5 frames so the
+    oracle finishes in seconds; bit-exact on every field."""
+    from fruid_b200.scene import Scene
+    from oracle_api import ODensitySim, OFluidSim
+    a = Scene(fb.FluidSim, fb.DensitySim, w, h, n_dyes=1)
+    b = Scene(OFluidSim, ODensitySim, w, h, n_dyes=1)
+    a.run(5)
+    b.run(5)
+    fa, fo = _scene_fields(a), _scene_fields(b)
+    for k in fa:
+        assert_bits(fa[k], fo[k], k)
