@@ -166,7 +166,10 @@ static int op_lin_solve(int b, float*& x, const float* x0, float*& scratch, cons
     int done = 0;
     for (int k = 0; k < nblocks; ++k) {
         const int T = (iters - done + (nblocks - k) - 1) / (nblocks - k);  // spread evenly
-        LAUNCH("k_jacobi_tile", st, TRY(jacobi_tile_launch(scratch, x, x0, g, a, c, b, T, st)));
+        prof_pre(st);
+        if (jacobi_tile_launch(scratch, x, x0, g, a, c, b, T, st) != 0)
+            return fail(FRUID_ERR_BAD_ARG, "fused sweeps T=%d not supported by the current tile config", T);
+        TRY(launched("k_jacobi_tile", st));
         done += T;
         float* t = x; x = scratch; scratch = t;
     }
@@ -432,6 +435,12 @@ extern "C" int fruid_density_sync(fruid_density_t* d) { NEED(d); CU(cudaStreamSy
 
 // Page-lock caller-owned host arrays (the Vec<f32> inside an Array2D has a fixed length for
 // the object's life) so uploads/downloads run at full PCIe rate.
+// Tile shape of the fused Jacobi kernel: R rows per warp x NW warps (tile = 128 x R*NW cells).
+extern "C" int fruid_set_tile_config(int rows_per_warp, int warps) {
+    if (jacobi_tile_set_cfg(rows_per_warp, warps) != 0)
+        return fail(FRUID_ERR_BAD_ARG, "unsupported tile config R=%d NW=%d", rows_per_warp, warps);
+    return 0;
+}
 extern "C" int fruid_host_register(void* p, size_t bytes) {
     if (!p || !bytes) return fail(FRUID_ERR_BAD_ARG, "null pointer or zero size");
     CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));

@@ -66,6 +66,9 @@ uint64_t fruid_kernel_launch_count(void);
 /* "sm_100a" build tag + version string. */
 const char *fruid_build_info(void);
 
+/* Tuning knob: tile shape of the fused Jacobi kernel (rows per warp x warps per CTA). */
+int fruid_set_tile_config(int rows_per_warp, int warps);
+
 /* Page-lock / unlock a caller-owned host array (e.g. the Vec<f32> inside an Array2D). */
 int fruid_host_register(void *p, size_t bytes);
 int fruid_host_unregister(void *p);
@@ -127,7 +130,8 @@ void *fruid_density_stream(fruid_density_t *d);
  * vel_step :181. */
 int fruid_op_add_source(float *x, const float *s, size_t w, size_t h, float dt);
 int fruid_op_set_bnd(int b, float *x, size_t w, size_t h);
-/* On return x holds the newest iterate and scratch the previous one (iters even). */
+/* On return x holds the newest iterate (iters must be even); scratch is unspecified
+ * (the reference never exposes it: src/lib.rs:213,252). */
 int fruid_op_lin_solve(int b, float *x, const float *x0, float *scratch, size_t w, size_t h, float a,
                        float c, int iters, int fused);
 int fruid_op_diffuse(int b, float *x, const float *x0, float *scratch, size_t w, size_t h,
