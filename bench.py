@@ -30,7 +30,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-DT, VISC, DIFF, ITERS = 1e-2, 1e-6, 1e-6, 20
+DT, VISC, DIFF, ITERS = 1e-2, 0.0, 0.0, 20  # dt, visc, diff of the reference scene (src/main.rs:110-112)
 SEED = 0x5EED0001
 
 

@@ -167,7 +167,7 @@ static int op_lin_solve(int b, float*& x, const float* x0, float*& scratch, cons
     for (int k = 0; k < nblocks; ++k) {
         const int T = (iters - done + (nblocks - k) - 1) / (nblocks - k);  // spread evenly
         prof_pre(st);
-        if (jacobi_tile_launch(scratch, x, x0, g, a, c, b, T, st) != 0)
+        if (jacobi_tile_launch(scratch, x, x0, g, a, c, b, T, 0, st) != 0)
             return fail(FRUID_ERR_BAD_ARG, "fused sweeps T=%d not supported by the current tile config", T);
         TRY(launched("k_jacobi_tile", st));
         done += T;
@@ -436,8 +436,8 @@ extern "C" int fruid_density_sync(fruid_density_t* d) { NEED(d); CU(cudaStreamSy
 // Page-lock caller-owned host arrays (the Vec<f32> inside an Array2D has a fixed length for
 // the object's life) so uploads/downloads run at full PCIe rate.
 // Tile shape of the fused Jacobi kernel: R rows per warp x NW warps (tile = 128 x R*NW cells).
-extern "C" int fruid_set_tile_config(int rows_per_warp, int warps) {
-    if (jacobi_tile_set_cfg(rows_per_warp, warps) != 0)
+extern "C" int fruid_set_tile_config(int rows_per_warp, int warps, int default_fused) {
+    if (jacobi_tile_set_cfg(rows_per_warp, warps, default_fused) != 0)
         return fail(FRUID_ERR_BAD_ARG, "unsupported tile config R=%d NW=%d", rows_per_warp, warps);
     return 0;
 }

@@ -1,12 +1,18 @@
 // jacobi_tile.cuh -- T fused Jacobi sweeps of lin_solve (src/lib.rs:46-71) per launch.
 //
-// Register-tile temporal blocking.  A CTA owns a tile of 128 columns x (R*NW) rows; warp
-// `wi` owns R consecutive rows, lane `l` owns 4 consecutive columns (one float4 per row).
-// The iterate x AND the right-hand side x0 live in registers for all T sweeps; x-neighbours
-// travel by warp shuffle, the two rows a warp needs from its neighbours go through a
+// Register-tile temporal blocking for sm_100a.  A CTA owns a tile of 128 columns x (R*NW)
+// rows; warp `wi` owns R consecutive rows, lane `l` owns 4 consecutive columns (one float4
+// per row).  The kernel is PERSISTENT (one CTA per SM looping over tiles): while tile i is
+// being swept, one elected thread has already issued the TMA loads (cp.async.bulk.tensor.2d,
+// mbarrier completion, zero fill outside the field) of tile i+1's x and x0 into shared
+// memory, so HBM latency and bandwidth are hidden behind the sweeps.  The iterate x lives in
+// REGISTERS for all T sweeps and so does the right-hand side x0 (both copied once per tile
+// from their TMA staging buffers), which keeps the shared-memory/shuffle (MIO) path free for
+// what cannot live in registers.  x-neighbours
+// travel by warp shuffle; the two rows a warp needs from its neighbour warps go through a
 // double-buffered shared-memory exchange (one __syncthreads per sweep).  HBM traffic per
 // launch is one read of x, one read of x0 and one write of the result (12 B/cell times the
-// halo overhead) instead of 12 B/cell per sweep.
+// halo overhead) instead of 12 B/cell per sweep; the kernel is issue-bound, not HBM-bound.
 //
 // Tiles overlap by 2H cells (H = T rounded up to even, so tile origins stay float4
 // aligned): after s sweeps the outermost s rings of a tile are stale, and only the cells
@@ -23,119 +29,190 @@
 // Arithmetic: sum = ((l + r) + u) + d; out = (x0 + a*sum) / c  (lib.rs:61-65), built from
 // __fadd_rn/__fmul_rn/__fdiv_rn only.  MODE_POW2 replaces the division by a multiplication
 // with 1/c when c is a power of two (bit-identical: same real value, same rounding);
-// MODE_ONE drops it when c == 1.  a*sum is always computed (0*inf, 1*NaN etc. must match).
+// MODE_ONE drops it when c == 1; MODE_POISSON additionally drops the multiplication by
+// a == 1 (1*sum == sum bit-for-bit).  Otherwise a*sum is always computed (0*inf etc.).
 #pragma once
+#include <cuda.h>
+
+#include <iterator>
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace fruid {
 
-enum : int { MODE_GENERAL = 0, MODE_POW2 = 1, MODE_ONE = 2 };
+enum : int { MODE_GENERAL = 0, MODE_POW2 = 1, MODE_ONE = 2, MODE_POISSON = 3 };
 
 struct TileArgs {
+    CUtensorMap tm_x0;  // 2-D map over x0: dims (pitch, h) f32, box (128, R*NW), zero OOB fill
+    CUtensorMap tm_x;   // same over the incoming iterate x
     float* out;
     const float* x;
-    const float* x0;
     Geom g;
-    float a, c;  // c holds 1/c in MODE_POW2
+    float a, c;  // c holds 1/c in MODE_POW2 / MODE_POISSON
     int b;       // bounds kind
     int T;       // sweeps in this launch
     int H;       // halo = T rounded up to even
     int SX, SY;  // tile strides = extent - 2H
     int ntx, nty;
+    int x_is_zero;  // the incoming iterate is identically +0 (pressure solve, lib.rs:152,160): skip its load
 };
 
+// One float4 row of the update.  t = l + r per component (scalar adds: the operands are
+// not register-pair aligned); the remaining adds and multiplies use the sm_100 packed
+// f32x2 instructions (FADD2 / FMUL2: two IEEE round-to-nearest operations per issue slot,
+// bit-identical to two scalar ones), which halves the issue pressure of this issue-bound
+// kernel.  Order of operations is exactly lib.rs:61-65: ((l + r) + u) + d, then
+// (x0 + a*sum) / c.
 template <int MODE>
-__device__ __forceinline__ float jac_upd(float z, float l, float r, float u, float d, float a, float c) {
-    const float sum = fadd(fadd(fadd(l, r), u), d);
-    const float v = fadd(z, fmul(a, sum));
-    if (MODE == MODE_GENERAL) return fdiv(v, c);
-    if (MODE == MODE_POW2) return fmul(v, c);
-    return v;
+__device__ __forceinline__ float4 jac_row(const float4 z, float t0, float t1, float t2, float t3, const float4 up,
+                                          const float4 dn, float a, float c) {
+    float2 s01 = __fadd2_rn(make_float2(t0, t1), make_float2(up.x, up.y));
+    float2 s23 = __fadd2_rn(make_float2(t2, t3), make_float2(up.z, up.w));
+    s01 = __fadd2_rn(s01, make_float2(dn.x, dn.y));
+    s23 = __fadd2_rn(s23, make_float2(dn.z, dn.w));
+    if (MODE != MODE_POISSON) {
+        // a*sum (for a == 1 the product is the sum itself, bit for bit).  SCALAR multiplies on
+        // purpose: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under
+        // -fmad=false, which would change the rounding (tests/test_abi_load.py greps for it).
+        s01 = make_float2(fmul(a, s01.x), fmul(a, s01.y));
+        s23 = make_float2(fmul(a, s23.x), fmul(a, s23.y));
+    }
+    s01 = __fadd2_rn(make_float2(z.x, z.y), s01);
+    s23 = __fadd2_rn(make_float2(z.z, z.w), s23);
+    if (MODE == MODE_GENERAL) return make_float4(fdiv(s01.x, c), fdiv(s01.y, c), fdiv(s23.x, c), fdiv(s23.y, c));
+    if (MODE == MODE_POW2 || MODE == MODE_POISSON) {
+        s01 = __fmul2_rn(s01, make_float2(c, c));
+        s23 = __fmul2_rn(s23, make_float2(c, c));
+    }
+    return make_float4(s01.x, s01.y, s23.x, s23.y);
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 sgn4(bool neg, float4 v) {
     return neg ? make_float4(-v.x, -v.y, -v.z, -v.w) : v;
 }
-__device__ __forceinline__ float comp(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+
+// ---- mbarrier / TMA primitives (PTX; SASS: SYNCS.*, UTMALDG) ------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// EDGE tiles: flags saying which of my components sit next to a domain border column
+// (gx == 1: left neighbour is border column 0; gx == w-2: right neighbour is column w-1).
+struct EdgeFlags { bool l1, r0, r1, r2, r3, negx, negy; int h; };
+
+// New value of one float4 row from its old value cc, the rows above/below and x0 (z).
+template <int MODE, bool EDGE>
+__device__ __forceinline__ float4 jac_row_full(float4 cc, float4 up, float4 dn, const float4 z, float a, float c,
+                                               const EdgeFlags& E, bool sub, int gy) {
+    const unsigned FULL = 0xffffffffu;
+    float lft = __shfl_up_sync(FULL, cc.w, 1);
+    float rgt = __shfl_down_sync(FULL, cc.x, 1);
+    float ly = cc.x, rx = cc.y, ry = cc.z, rz = cc.w;
+    if (EDGE) {
+        if (sub && gy == 1) up = sgn4(E.negy, cc);           // row 0 = sy * row 1       (lib.rs:36)
+        if (sub && gy == E.h - 2) dn = sgn4(E.negy, cc);     // row ny+1 = sy * row ny   (lib.rs:37)
+        if (sub && E.l1) ly = sgn(E.negx, cc.y);             // col 0 = sx * col 1       (lib.rs:31)
+        if (sub && E.r0) rx = sgn(E.negx, cc.x);             // col nx+1 = sx * col nx   (lib.rs:32)
+        if (sub && E.r1) ry = sgn(E.negx, cc.y);
+        if (sub && E.r2) rz = sgn(E.negx, cc.z);
+        if (sub && E.r3) rgt = sgn(E.negx, cc.w);
+    }
+    const float t0 = fadd(lft, rx), t1 = fadd(ly, ry), t2 = fadd(cc.y, rz), t3 = fadd(cc.z, rgt);  // l + r
+    return jac_row<MODE>(z, t0, t1, t2, t3, up, dn, a, c);
+}
 
 template <int R, int NW, int MODE, bool EDGE>
-__device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, float4 (*halo)[NW][2][32]) {
+__device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int ky, float4 (&v)[R + 1],
+                                                 const float4 (&z)[R], float4* __restrict__ halo) {
     constexpr int TH = R * NW;
+    constexpr int HB = (NW * 2 + 2) * 32;  // float4 slots per halo buffer (one guard row at each end)
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const Geom& g = A.g;
-    const int kx = blockIdx.x, ky = blockIdx.y;
     const int ox = kx * A.SX, oy = ky * A.SY;
     const int gx0 = ox + 4 * lane;  // global column of component .x
     const int gyw = oy + wi * R;    // global row of this warp's row 0
     const bool negx = (A.b == B_NEGX), negy = (A.b == B_NEGY);
     const float a = A.a, c = A.c;
 
-    float4 xr[R], zr[R];
-    const bool colok = gx0 < (int)g.pitch;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int gy = gyw + r;
-        if (colok && gy < g.h) {
-            const size_t k = (size_t)gy * g.pitch + gx0;
-            xr[r] = ldg4(A.x + k);
-            zr[r] = ldg4(A.x0 + k);
-        } else {
-            xr[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-            zr[r] = xr[r];
-        }
-    }
-
-    // EDGE tiles: which of my components sit next to a domain border column
-    // (gx == 1: left neighbour is border column 0; gx == w-2: right neighbour is column w-1).
-    bool l1 = false, r0 = false, r1 = false, r2 = false, r3 = false;
+    EdgeFlags E;
+    E.l1 = E.r0 = E.r1 = E.r2 = E.r3 = false;
+    E.negx = negx; E.negy = negy; E.h = g.h;
     if (EDGE) {
-        l1 = (gx0 + 1 == 1);  // ox == 0 && lane == 0 (tile origins are multiples of 4)
-        r0 = (gx0 + 0 == g.w - 2); r1 = (gx0 + 1 == g.w - 2); r2 = (gx0 + 2 == g.w - 2); r3 = (gx0 + 3 == g.w - 2);
+        E.l1 = (gx0 + 1 == 1);  // ox == 0 && lane == 0 (tile origins are multiples of 4)
+        E.r0 = (gx0 + 0 == g.w - 2); E.r1 = (gx0 + 1 == g.w - 2); E.r2 = (gx0 + 2 == g.w - 2); E.r3 = (gx0 + 3 == g.w - 2);
     }
 
-    for (int s = 1; s <= A.T; ++s) {
-        const int p = s & 1;
-        halo[p][wi][0][lane] = xr[0];
-        halo[p][wi][1][lane] = xr[R - 1];
-        __syncthreads();
-        const float4 htop = (wi > 0) ? halo[p][wi - 1][1][lane] : xr[0];
-        const float4 hbot = (wi < NW - 1) ? halo[p][wi + 1][0][lane] : xr[R - 1];
-        const bool sub = EDGE && (s > 1);
-        float4 prev = htop;
+    // My top-row slot in halo buffer 0 (+32: my bottom row).  Slot -32 is the bottom row of the
+    // warp above, slot +64 the top row of the warp below; warp 0 / NW-1 hit the guard rows
+    // (stale values: those rows are outside the tile and never feed a stored cell).
+    float4* const hw = halo + (wi * 2 + 1) * 32 + lane;
+
+    for (int s = 1; s <= A.T; s += 2) {
+        {   // ---- down sweep: rows in v[1..R] -> v[0..R-1] ----
+            hw[HB] = v[1];
+            hw[HB + 32] = v[R];
+            __syncthreads();
+            v[0] = hw[HB - 32];
+            const float4 hbot = hw[HB + 64];
+            const bool sub = EDGE && (s > 1);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float4 cc = xr[r];
-            float4 up = prev;
-            float4 dn = (r == R - 1) ? hbot : xr[r + 1];
-            float lft = __shfl_up_sync(FULL, cc.w, 1);
-            float rgt = __shfl_down_sync(FULL, cc.x, 1);
-            float ly = cc.x, rx = cc.y, ry = cc.z, rz = cc.w;
-            if (EDGE) {
-                const int gy = gyw + r;
-                if (sub && gy == 1) up = sgn4(negy, cc);           // row 0 = sy * row 1       (lib.rs:36)
-                if (sub && gy == g.h - 2) dn = sgn4(negy, cc);     // row ny+1 = sy * row ny   (lib.rs:37)
-                if (sub && l1) ly = sgn(negx, cc.y);               // col 0 = sx * col 1       (lib.rs:31)
-                if (sub && r0) rx = sgn(negx, cc.x);               // col nx+1 = sx * col nx   (lib.rs:32)
-                if (sub && r1) ry = sgn(negx, cc.y);
-                if (sub && r2) rz = sgn(negx, cc.z);
-                if (sub && r3) rgt = sgn(negx, cc.w);
-            }
-            float4 n;
-            n.x = jac_upd<MODE>(zr[r].x, lft, rx, up.x, dn.x, a, c);
-            n.y = jac_upd<MODE>(zr[r].y, ly, ry, up.y, dn.y, a, c);
-            n.z = jac_upd<MODE>(zr[r].z, cc.y, rz, up.z, dn.z, a, c);
-            n.w = jac_upd<MODE>(zr[r].w, cc.z, rgt, up.w, dn.w, a, c);
-            prev = cc;
-            xr[r] = n;
+            for (int r = 1; r <= R; ++r)
+                v[r - 1] = jac_row_full<MODE, EDGE>(v[r], v[r - 1], (r == R) ? hbot : v[r + 1], z[r - 1], a, c, E,
+                                                    sub, gyw + r - 1);
+        }
+        if (s + 1 > A.T) {  // odd T: move the rows back to v[1..R] for the store phase
+#pragma unroll
+            for (int r = R; r >= 1; --r) v[r] = v[r - 1];
+            break;
+        }
+        {   // ---- up sweep: rows in v[0..R-1] -> v[1..R] ----
+            hw[0] = v[0];
+            hw[32] = v[R - 1];
+            __syncthreads();
+            v[R] = hw[64];
+            const float4 htop = hw[-32];
+#pragma unroll
+            for (int r = R - 1; r >= 0; --r)
+                v[r + 1] = jac_row_full<MODE, EDGE>(v[r], (r == 0) ? htop : v[r - 1], v[r + 1], z[r], a, c, E, EDGE,
+                                                    gyw + r);
         }
     }
+    float4* const xr = v + 1;  // rows 0..R-1 of this warp
 
     // ---- store the cells that are H away from every non-domain tile edge -----------------
+    (void)FULL;
     const bool lastx = (kx == A.ntx - 1), lasty = (ky == A.nty - 1);
     const int xlo = (kx == 0) ? 0 : ox + A.H, xhi = lastx ? g.w : ox + 128 - A.H;   // [xlo, xhi)
     const int ylo = (ky == 0) ? 1 : oy + A.H, yhi = lasty ? g.h - 1 : oy + TH - A.H;  // interior rows only
+    const bool v0 = gx0 + 0 >= xlo && gx0 + 0 < xhi, v1 = gx0 + 1 >= xlo && gx0 + 1 < xhi;
+    const bool v2 = gx0 + 2 >= xlo && gx0 + 2 < xhi, v3 = gx0 + 3 >= xlo && gx0 + 3 < xhi;
+    const bool vall = v0 && v1 && v2 && v3;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int gy = gyw + r;
@@ -152,9 +229,7 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, float4 (*hal
             if (gx0 + 3 == g.w - 1) f.w = sgn(negx, f.z);
         }
         float* row = A.out + (size_t)gy * g.pitch;
-        const bool v0 = gx0 + 0 >= xlo && gx0 + 0 < xhi, v1 = gx0 + 1 >= xlo && gx0 + 1 < xhi;
-        const bool v2 = gx0 + 2 >= xlo && gx0 + 2 < xhi, v3 = gx0 + 3 >= xlo && gx0 + 3 < xhi;
-        if (v0 && v1 && v2 && v3) {
+        if (vall) {
             *reinterpret_cast<float4*>(row + gx0) = f;
         } else {
             if (v0) row[gx0 + 0] = f.x;
@@ -186,20 +261,129 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, float4 (*hal
     }
 }
 
+template <int R, int NW>
+constexpr size_t jacobi_tile_smem_bytes() {
+    // TMA staging of the next tile's x0 and x + halo exchange (2 buffers, NW*2+2 rows of 512 B) + mbarrier
+    return (size_t)2 * R * NW * 512 + (size_t)2 * (NW * 2 + 2) * 512 + 16;
+}
+
 template <int R, int NW, int MODE>
-__global__ void __launch_bounds__(NW * 32) k_jacobi_tile(TileArgs A) {
-    __shared__ float4 halo[2][NW][2][32];
-    const int ox = blockIdx.x * A.SX, oy = blockIdx.y * A.SY;
-    const bool edge = (blockIdx.x == 0) || (blockIdx.y == 0) || (ox + 128 >= A.g.w - 1) || (oy + R * NW >= A.g.h - 1);
-    if (edge)
-        jacobi_tile_body<R, NW, MODE, true>(A, halo);
-    else
-        jacobi_tile_body<R, NW, MODE, false>(A, halo);
+__global__ void __launch_bounds__(NW * 32, 1) k_jacobi_tile(const __grid_constant__ TileArgs A) {
+    constexpr int TH = R * NW;
+    constexpr uint32_t TILE_BYTES = TH * 512;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* const zs = reinterpret_cast<float*>(smem_raw);                        // [TH][128] x0 staging (TMA dst)
+    float* const xs = reinterpret_cast<float*>(smem_raw + (size_t)TILE_BYTES);   // [TH][128] x staging  (TMA dst)
+    float4* const halo = reinterpret_cast<float4*>(smem_raw + (size_t)2 * TILE_BYTES);
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)2 * TILE_BYTES + (size_t)2 * (NW * 2 + 2) * 512);
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int ntiles = A.ntx * A.nty;
+    const uint32_t tx_bytes = A.x_is_zero ? TILE_BYTES : 2 * TILE_BYTES;
+
+    int tile = blockIdx.x;
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        if (tile < ntiles) {
+            const int kx = tile % A.ntx, ky = tile / A.ntx;
+            mbar_expect_tx(mbar, tx_bytes);
+            tma_load_2d(zs, &A.tm_x0, kx * A.SX, ky * A.SY, mbar);
+            if (!A.x_is_zero) tma_load_2d(xs, &A.tm_x, kx * A.SX, ky * A.SY, mbar);
+        }
+    }
+    __syncthreads();  // barrier init visible to every waiter
+
+    uint32_t phase = 0;
+    for (; tile < ntiles; tile += gridDim.x) {
+        const int kx = tile % A.ntx, ky = tile / A.ntx;
+        mbar_wait(mbar, phase);  // this tile's x0 (and x) have landed in the staging buffers
+        phase ^= 1u;
+
+        // Staging -> registers: the iterate and the right-hand side stay there for all T sweeps.
+        float4 v[R + 1], z[R];
+        {
+            const float4* xrow = reinterpret_cast<const float4*>(xs) + (wi * R) * 32 + lane;
+            const float4* zrow = reinterpret_cast<const float4*>(zs) + (wi * R) * 32 + lane;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                v[r + 1] = A.x_is_zero ? make_float4(0.f, 0.f, 0.f, 0.f) : xrow[r * 32];
+                z[r] = zrow[r * 32];
+            }
+            v[0] = v[1];
+        }
+        __syncthreads();  // staging buffers are free again (and the previous tile's halo reads are done)
+        const int next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < ntiles) {  // prefetch the next tile behind this tile's sweeps
+            const int nkx = next % A.ntx, nky = next / A.ntx;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before async writes
+            mbar_expect_tx(mbar, tx_bytes);
+            tma_load_2d(zs, &A.tm_x0, nkx * A.SX, nky * A.SY, mbar);
+            if (!A.x_is_zero) tma_load_2d(xs, &A.tm_x, nkx * A.SX, nky * A.SY, mbar);
+        }
+        const int ox = kx * A.SX, oy = ky * A.SY;
+        const bool edge = (kx == 0) || (ky == 0) || (ox + 128 >= A.g.w - 1) || (oy + TH >= A.g.h - 1);
+        if (edge)
+            jacobi_tile_body<R, NW, MODE, true>(A, kx, ky, v, z, halo);
+        else
+            jacobi_tile_body<R, NW, MODE, false>(A, kx, ky, v, z, halo);
+    }
 }
 
 // ---- host side -----------------------------------------------------------------------------
 struct TileCfg { int R, NW; };
-static TileCfg g_tile_cfg = {8, 8};
+static TileCfg g_tile_cfg = {8, 16};
+static int g_tile_default_T = 10;
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda).
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+struct TmKey {
+    const void* p; size_t pitch; int h; int th;
+    bool operator==(const TmKey& o) const { return p == o.p && pitch == o.pitch && h == o.h && th == o.th; }
+};
+struct TmKeyHash {
+    size_t operator()(const TmKey& k) const {
+        return std::hash<const void*>()(k.p) ^ (k.pitch * 1315423911u) ^ ((size_t)k.h << 20) ^ (size_t)k.th;
+    }
+};
+static std::mutex g_tm_mu;
+static std::unordered_map<TmKey, CUtensorMap, TmKeyHash> g_tm_cache;
+
+// Tensor map of a field for (128 x th) boxes.  Returns 0 or -4 (CUDA error).
+static int tile_tensor_map(const float* base, size_t pitch, int h, int th, CUtensorMap* out) {
+    std::lock_guard<std::mutex> lk(g_tm_mu);
+    const TmKey key{base, pitch, h, th};
+    auto it = g_tm_cache.find(key);
+    if (it != g_tm_cache.end()) { *out = it->second; return 0; }
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return -4;
+    const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)h};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+    const cuuint32_t box[2] = {128u, (cuuint32_t)th};
+    const cuuint32_t estr[2] = {1u, 1u};
+    CUtensorMap tm;
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return -4;
+    if (g_tm_cache.size() > 4096) g_tm_cache.clear();
+    g_tm_cache.emplace(key, tm);
+    *out = tm;
+    return 0;
+}
 
 static inline int jacobi_tile_max_T(int R, int NW) {
     const int th = R * NW;
@@ -209,20 +393,40 @@ static inline int jacobi_tile_max_T(int R, int NW) {
 
 static inline int jacobi_tile_default_fused(const Geom& g, int iters) {
     (void)g;
-    int T = 10;
+    int T = g_tile_default_T;
     const int mx = jacobi_tile_max_T(g_tile_cfg.R, g_tile_cfg.NW);
     if (T > mx) T = mx;
     if (T > iters) T = iters;
     return T < 1 ? 1 : T;
 }
 
+template <int R, int NW, int MODE>
+static int jacobi_tile_launch_mode(const TileArgs& A, cudaStream_t st) {
+    constexpr size_t smem = jacobi_tile_smem_bytes<R, NW>();
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_jacobi_tile<R, NW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return -4;
+        attr_set = true;
+    }
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            return -4;
+    }
+    const int ntiles = A.ntx * A.nty;
+    dim3 grid(ntiles < num_sms ? ntiles : num_sms), block(NW * 32);
+    k_jacobi_tile<R, NW, MODE><<<grid, block, smem, st>>>(A);
+    return 0;
+}
+
 template <int R, int NW>
 static int jacobi_tile_launch_cfg(const TileArgs& A, int mode, cudaStream_t st) {
-    dim3 grid(A.ntx, A.nty), block(NW * 32);
-    if (mode == MODE_GENERAL) k_jacobi_tile<R, NW, MODE_GENERAL><<<grid, block, 0, st>>>(A);
-    else if (mode == MODE_POW2) k_jacobi_tile<R, NW, MODE_POW2><<<grid, block, 0, st>>>(A);
-    else k_jacobi_tile<R, NW, MODE_ONE><<<grid, block, 0, st>>>(A);
-    return 0;
+    if (mode == MODE_GENERAL) return jacobi_tile_launch_mode<R, NW, MODE_GENERAL>(A, st);
+    if (mode == MODE_POW2) return jacobi_tile_launch_mode<R, NW, MODE_POW2>(A, st);
+    if (mode == MODE_POISSON) return jacobi_tile_launch_mode<R, NW, MODE_POISSON>(A, st);
+    return jacobi_tile_launch_mode<R, NW, MODE_ONE>(A, st);
 }
 
 static inline int tiles_needed(int extent, int tile, int stride) {
@@ -230,13 +434,17 @@ static inline int tiles_needed(int extent, int tile, int stride) {
     return (extent - tile + stride - 1) / stride + 1;
 }
 
-// Returns 0 or a negative fruid_status (-7 = bad argument).
+#define FRUID_TILE_CONFIGS(X) X(8, 16) X(10, 16) X(6, 16) X(6, 20) X(7, 20) X(5, 24) X(4, 24) X(8, 12) X(4, 16)
+
+// Returns 0 or a negative fruid_status (-7 = bad argument, -4 = CUDA error).
 static int jacobi_tile_launch(float* out, const float* x, const float* x0, const Geom& g, float a, float c, int b, int T,
-                              cudaStream_t st) {
+                              int x_is_zero, cudaStream_t st) {
     const int R = g_tile_cfg.R, NW = g_tile_cfg.NW, TH = R * NW;
     if (T < 1 || T > jacobi_tile_max_T(R, NW)) return -7;
     TileArgs A;
-    A.out = out; A.x = x; A.x0 = x0; A.g = g; A.a = a; A.b = b; A.T = T;
+    if (int r = tile_tensor_map(x0, g.pitch, g.h, TH, &A.tm_x0)) return r;
+    if (int r = tile_tensor_map(x, g.pitch, g.h, TH, &A.tm_x)) return r;
+    A.out = out; A.x = x; A.g = g; A.a = a; A.b = b; A.T = T; A.x_is_zero = x_is_zero;
     A.H = T + (T & 1);
     A.SX = 128 - 2 * A.H;
     A.SY = TH - 2 * A.H;
@@ -249,25 +457,21 @@ static int jacobi_tile_launch(float* out, const float* x, const float* x0, const
     } else {
         int e = 0;
         const float m = frexpf(c, &e);
-        if (m == 0.5f && e > -100 && e < 100) { mode = MODE_POW2; A.c = 1.0f / c; }  // exact reciprocal
+        if (m == 0.5f && e > -100 && e < 100) {  // c = 2^k: multiply by the exact reciprocal
+            mode = (a == 1.0f) ? MODE_POISSON : MODE_POW2;
+            A.c = 1.0f / c;
+        }
     }
-#define FRUID_TILE_CASE(r, nw) if (R == r && NW == nw) return jacobi_tile_launch_cfg<r, nw>(A, mode, st)
-    FRUID_TILE_CASE(8, 8);
-    FRUID_TILE_CASE(8, 16);
-    FRUID_TILE_CASE(12, 8);
-    FRUID_TILE_CASE(12, 16);
-    FRUID_TILE_CASE(16, 8);
-    FRUID_TILE_CASE(16, 12);
-    FRUID_TILE_CASE(6, 16);
-    FRUID_TILE_CASE(4, 16);
+#define FRUID_TILE_CASE(r, nw) if (R == r && NW == nw) return jacobi_tile_launch_cfg<r, nw>(A, mode, st);
+    FRUID_TILE_CONFIGS(FRUID_TILE_CASE)
 #undef FRUID_TILE_CASE
     return -7;
 }
 
-static inline int jacobi_tile_set_cfg(int R, int NW) {
-    const int ok[][2] = {{8, 8}, {8, 16}, {12, 8}, {12, 16}, {16, 8}, {16, 12}, {6, 16}, {4, 16}};
-    for (auto& p : ok)
-        if (p[0] == R && p[1] == NW) { g_tile_cfg = {R, NW}; return 0; }
+static inline int jacobi_tile_set_cfg(int R, int NW, int T) {
+#define FRUID_TILE_OK(r, nw) if (R == r && NW == nw) { g_tile_cfg = {R, NW}; if (T > 0) g_tile_default_T = T; return 0; }
+    FRUID_TILE_CONFIGS(FRUID_TILE_OK)
+#undef FRUID_TILE_OK
     return -7;
 }
 

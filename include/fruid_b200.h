@@ -66,8 +66,9 @@ uint64_t fruid_kernel_launch_count(void);
 /* "sm_100a" build tag + version string. */
 const char *fruid_build_info(void);
 
-/* Tuning knob: tile shape of the fused Jacobi kernel (rows per warp x warps per CTA). */
-int fruid_set_tile_config(int rows_per_warp, int warps);
+/* Tuning knob: tile shape of the fused Jacobi kernel (rows per warp x warps per CTA; the tile
+ * is 128 x rows_per_warp*warps cells) and the default number of fused sweeps (0 = keep). */
+int fruid_set_tile_config(int rows_per_warp, int warps, int default_fused);
 
 /* Page-lock / unlock a caller-owned host array (e.g. the Vec<f32> inside an Array2D). */
 int fruid_host_register(void *p, size_t bytes);

@@ -16,9 +16,10 @@ from fruid_b200 import _lib  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=4096)
 ap.add_argument("--iters", type=int, default=20)
-ap.add_argument("--cfgs", default="8x8,8x16,12x8,12x16,16x8,16x12,6x16,4x16")
+ap.add_argument("--cfgs", default="8x16,10x16,6x16,6x20,7x20,5x24,4x24,8x12,4x16")
 ap.add_argument("--fused", default="1,2,4,6,10,20")
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--modes", default="poisson,general,inviscid")
 args = ap.parse_args()
 
 w = h = args.size
@@ -32,9 +33,11 @@ st = torch.cuda.current_stream()
 L = _lib.lib
 rows = []
 for (name, a, c) in (("poisson a=1 c=4", 1.0, 4.0), ("general a=.17 c=1.67", 0.1676, 1.6704), ("inviscid a=0 c=1", 0.0, 1.0)):
+    if name.split()[0] not in args.modes.split(","):
+        continue
     for cfg in args.cfgs.split(","):
         R, NW = map(int, cfg.split("x"))
-        _lib.check(L.fruid_set_tile_config(R, NW))
+        _lib.check(L.fruid_set_tile_config(R, NW, 0))
         for T in map(int, args.fused.split(",")):
             if T != 1 and cfg != args.cfgs.split(",")[0] and False:
                 continue
