@@ -315,45 +315,48 @@ def run_b200(args):
 
 
 def run_e2e(args, fb, torch, sc, w, h):
-    """Scene step through FluidSim / DensitySim (the call a user makes) with host buffers: every
-    step rewrites the three source fields on the host (page-locked mirrors), which are uploaded by
-    step(), and reads the resulting density back to the host."""
+    """Scene step through the C ABI with HOST buffers (what the Rust shim's step() does when the
+    caller has rewritten its sources): every step uploads the three source fields (u_prev, v_prev,
+    dens_prev) from page-locked host arrays, runs FluidSim::step + DensitySim::step, and downloads
+    the resulting density to the host.  Wall clock over n steps, synchronised on both sides."""
     from fruid_b200 import _lib
+    L = _lib.lib
     sim, den = fb.FluidSim(w, h), fb.DensitySim(w, h)
     if args.fused is not None:
         sim.set_fused_sweeps(args.fused)
         den.set_fused_sweeps(args.fused)
     for name, field in (("u", 0), ("v", 1)):
-        _lib.check(_lib.lib.fruid_fluid_upload(sim._h, field, _lib.ptr(sc[name])))
-    _lib.check(_lib.lib.fruid_density_upload(den._h, 0, _lib.ptr(sc["dens"])))
-    srcs = (sc["u_prev"].reshape(-1), sc["v_prev"].reshape(-1), sc["dens_prev"].reshape(-1))
+        _lib.check(L.fruid_fluid_upload(sim._h, field, _lib.ptr(sc[name])))
+    _lib.check(L.fruid_density_upload(den._h, 0, _lib.ptr(sc["dens"])))
+    host = {k: np.ascontiguousarray(sc[k]) for k in ("u_prev", "v_prev", "dens_prev")}
+    out = np.empty((h, w), np.float32)
+    pinned = [a for a in (*host.values(), out) if L.fruid_host_register(a.ctypes.data, a.nbytes) == 0]
     nbytes = w * h * 4
 
     def step():
-        u0, v0 = sim.uv_mut()
-        u0.copy_from(srcs[0])               # host writes into the pinned mirrors ...
-        v0.copy_from(srcs[1])
-        den.density_mut().copy_from(srcs[2])
-        sim.step(DT, VISC)                  # ... uploaded here (h2d inside the timed region)
-        den.step(sim.uv(), DT, DIFF)
-        return den.density().data()         # d2h of the step's result
+        _lib.check(L.fruid_fluid_upload(sim._h, _lib.U_PREV, _lib.ptr(host["u_prev"])))      # h2d
+        _lib.check(L.fruid_fluid_upload(sim._h, _lib.V_PREV, _lib.ptr(host["v_prev"])))      # h2d
+        _lib.check(L.fruid_density_upload(den._h, _lib.DENS_PREV, _lib.ptr(host["dens_prev"])))  # h2d
+        _lib.check(L.fruid_fluid_step(sim._h, DT, VISC))
+        _lib.check(L.fruid_density_step_dev(den._h, sim._h, DT, DIFF))
+        _lib.check(L.fruid_density_download(den._h, _lib.DENS, _lib.ptr(out)))              # d2h (blocks)
 
-    # first call downloads stale mirrors once; warm up
     for _ in range(2):
         step()
     torch.cuda.synchronize()
     n = max(1, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(n):
-        out = step()
+        step()
     torch.cuda.synchronize()
     sec = time.perf_counter() - t0
-    assert np.isfinite(out[:: max(1, out.size // 4096)]).all()
+    ok = bool(np.isfinite(out[:: max(1, h // 64), :: max(1, w // 64)]).all())
+    for a in pinned:
+        L.fruid_host_unregister(a.ctypes.data)
     return {"value": w * h * n / sec, "unit": "cell-steps/s", "h2d_bytes_per_step": 3 * nbytes,
-            "d2h_bytes_per_step": nbytes, "steps": n,
-            "note": "per step: the u_prev, v_prev and dens_prev source fields are rewritten on the host (copy into "
-                    "the page-locked mirrors, inside the timed region) and uploaded by step(); density() is read "
-                    "back to the host; wall-clock over n steps, synchronised on both sides"}
+            "d2h_bytes_per_step": nbytes, "steps": n, "finite": ok, "pinned_host": len(pinned) == 4,
+            "note": "per step: h2d of the u_prev, v_prev and dens_prev source fields, FluidSim::step + "
+                    "DensitySim::step, d2h of density(); through the C ABI with host buffers"}
 
 
 def run_b200_multi(args, fb, dist, rank, world, local):

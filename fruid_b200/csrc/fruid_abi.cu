@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "kernels_basic.cuh"
 #include "kernels_serial.cuh"
+#include "kernels_vec.cuh"
 #include "jacobi_tile.cuh"
 
 using namespace fruid;
@@ -125,10 +126,14 @@ static inline size_t pitch_for(size_t w) { return (w + 31) / 32 * 32; }
 static inline bool degenerate(const Geom& g) { return g.nx < 1 || g.ny < 1; }
 static inline dim3 cell_block() { return dim3(128, 2); }
 static inline dim3 cell_grid(int cx, int cy) { return dim3((cx + 127) / 128, (cy + 1) / 2); }
+// float4-per-thread kernels: a warp covers 128 columns of one interior row
+static inline dim3 vec_block() { return dim3(32, 8); }
+static inline dim3 vec_grid(const Geom& g) { return dim3(((g.w + 3) / 4 + 31) / 32, (g.ny + 7) / 8); }
 
 static int op_add_source(float* x1, const float* s1, float* x2, const float* s2, const Geom& g, float dt,
                          cudaStream_t st) {
-    LAUNCH("k_add_source", st, k_add_source<<<cell_grid(g.w, g.h), cell_block(), 0, st>>>(x1, s1, x2, s2, g, dt));
+    const size_t n4 = g.pitch * (size_t)g.h / 4;
+    LAUNCH("k_add_source4", st, k_add_source4<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x1, s1, x2, s2, n4, dt));
     return 0;
 }
 
@@ -146,15 +151,18 @@ static int op_set_bnd(int b, float* x, const Geom& g, cudaStream_t st) {
 // buffer holding the newest iterate (the two are exchanged when the number of launches
 // is odd), so the caller's field roles follow the data and nothing is copied.
 // fused = sweeps per launch (1 = k_jacobi1; >1 = register-tile kernel of jacobi_tile.cuh).
+static inline int resolve_fused(const Geom& g, int iters, int fused) {
+    if (fused <= 0) fused = jacobi_tile_default_fused(g, iters);
+    return fused > iters ? iters : fused;
+}
 static int op_lin_solve(int b, float*& x, const float* x0, float*& scratch, const Geom& g, float a, float c,
-                        int iters, int fused, cudaStream_t st) {
+                        int iters, int fused, cudaStream_t st, bool x_is_zero = false) {
     if (iters < 2 || (iters & 1)) return fail(FRUID_ERR_ODD_ITERATIONS, "iterations must be even and >= 2, got %d", iters);
     if (degenerate(g)) {
         LAUNCH("k_serial_lin_solve", st, k_serial_lin_solve<<<1, 1, 0, st>>>(x, x0, scratch, g, a, c, b, iters));
         return 0;
     }
-    if (fused <= 0) fused = jacobi_tile_default_fused(g, iters);
-    if (fused > iters) fused = iters;
+    fused = resolve_fused(g, iters, fused);
     if (fused == 1) {
         for (int it = 0; it < iters; ++it) {
             LAUNCH("k_jacobi1", st, k_jacobi1<<<cell_grid(g.nx, g.ny), cell_block(), 0, st>>>(scratch, x, x0, g, a, c, b));
@@ -167,7 +175,7 @@ static int op_lin_solve(int b, float*& x, const float* x0, float*& scratch, cons
     for (int k = 0; k < nblocks; ++k) {
         const int T = (iters - done + (nblocks - k) - 1) / (nblocks - k);  // spread evenly
         prof_pre(st);
-        if (jacobi_tile_launch(scratch, x, x0, g, a, c, b, T, 0, st) != 0)
+        if (jacobi_tile_launch(scratch, x, x0, g, a, c, b, T, (x_is_zero && k == 0) ? 1 : 0, st) != 0)
             return fail(FRUID_ERR_BAD_ARG, "fused sweeps T=%d not supported by the current tile config", T);
         TRY(launched("k_jacobi_tile", st));
         done += T;
@@ -199,9 +207,9 @@ static int op_advect(int nf, float* const* d, const float* const* d0, const int*
     AdvectArgs a{};
     for (int f = 0; f < nf; ++f) { a.d[f] = d[f]; a.d0[f] = d0[f]; a.b[f] = b[f]; }
     if (nf == 2)
-        LAUNCH("k_advect2", st, k_advect<2><<<cell_grid(g.nx, g.ny), cell_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax));
+        LAUNCH("k_advect4x2", st, k_advect4<2><<<vec_grid(g), vec_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax));
     else
-        LAUNCH("k_advect1", st, k_advect<1><<<cell_grid(g.nx, g.ny), cell_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax));
+        LAUNCH("k_advect4x1", st, k_advect4<1><<<vec_grid(g), vec_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax));
     return 0;
 }
 
@@ -213,10 +221,14 @@ static int op_project(float* u, float* v, float*& p, float* div, float*& scratch
         return 0;
     }
     const float sx = -0.5f / (float)g.nx, sy = -0.5f / (float)g.ny;  // lib.rs:156-157
-    LAUNCH("k_divergence", st, k_divergence<<<cell_grid(g.nx, g.ny), cell_block(), 0, st>>>(div, p, u, v, g, sx, sy));
-    TRY(op_lin_solve(B_POSITIVE, p, div, scratch, g, 1.0f, 4.0f, iters, fused, st));  // lib.rs:162
+    // p is zeroed at lib.rs:152,160 (interior, then border/corners from the zero interior): with
+    // the fused solver the zero field is not materialised, the first block is told instead.
+    const bool p_implicit_zero = resolve_fused(g, iters, fused) > 1;
+    LAUNCH("k_divergence4", st,
+           k_divergence4<<<vec_grid(g), vec_block(), 0, st>>>(div, p_implicit_zero ? nullptr : p, u, v, g, sx, sy));
+    TRY(op_lin_solve(B_POSITIVE, p, div, scratch, g, 1.0f, 4.0f, iters, fused, st, p_implicit_zero));  // lib.rs:162
     const float gx = -0.5f * (float)g.nx, gy = -0.5f * (float)g.ny;  // lib.rs:164-165
-    LAUNCH("k_gradient", st, k_gradient<<<cell_grid(g.nx, g.ny), cell_block(), 0, st>>>(u, v, p, g, gx, gy));
+    LAUNCH("k_gradient4", st, k_gradient4<<<vec_grid(g), vec_block(), 0, st>>>(u, v, p, g, gx, gy));
     return 0;
 }
 
