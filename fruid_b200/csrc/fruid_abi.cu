@@ -156,7 +156,8 @@ static inline int resolve_fused(const Geom& g, int iters, int fused) {
     return fused > iters ? iters : fused;
 }
 static int op_lin_solve(int b, float*& x, const float* x0, float*& scratch, const Geom& g, float a, float c,
-                        int iters, int fused, cudaStream_t st, bool x_is_zero = false) {
+                        int iters, int fused, cudaStream_t st, bool x_is_zero = false, bool fuse_src = false,
+                        float src_dt = 0.f, float* z_tmp = nullptr) {
     if (iters < 2 || (iters & 1)) return fail(FRUID_ERR_ODD_ITERATIONS, "iterations must be even and >= 2, got %d", iters);
     if (degenerate(g)) {
         LAUNCH("k_serial_lin_solve", st, k_serial_lin_solve<<<1, 1, 0, st>>>(x, x0, scratch, g, a, c, b, iters));
@@ -175,7 +176,9 @@ static int op_lin_solve(int b, float*& x, const float* x0, float*& scratch, cons
     for (int k = 0; k < nblocks; ++k) {
         const int T = (iters - done + (nblocks - k) - 1) / (nblocks - k);  // spread evenly
         prof_pre(st);
-        if (jacobi_tile_launch(scratch, x, x0, g, a, c, b, T, (x_is_zero && k == 0) ? 1 : 0, st) != 0)
+        const bool fs = fuse_src && k == 0;  // first block also performs add_source(x0, x, dt) -> z_tmp
+        if (jacobi_tile_launch(scratch, x, (fuse_src && k > 0) ? z_tmp : x0, g, a, c, b, T, (x_is_zero && k == 0) ? 1 : 0, st,
+                               fs ? 1 : 0, src_dt, (fs && nblocks > 1) ? z_tmp : nullptr) != 0)
             return fail(FRUID_ERR_BAD_ARG, "fused sweeps T=%d not supported by the current tile config", T);
         TRY(launched("k_jacobi_tile", st));
         done += T;
@@ -190,6 +193,21 @@ static int op_diffuse(int b, float*& x, const float* x0, float*& scratch, const 
     const float a = ((dt * diff) * (float)g.nx) * (float)g.ny;
     const float c = 1.0f + 4.0f * a;
     return op_lin_solve(b, x, x0, scratch, g, a, c, iters, fused, st);
+}
+
+// add_source(x0, x, dt) followed by diffuse(b, x, x0, ...) (lib.rs:172-175, 190-197: the source
+// field is also the initial iterate of the solve).  With the fused solver the add is folded into
+// the first block (registers) and x0 itself is left untouched -- its updated value would be dead:
+// the callers overwrite x0 right after (project zeroes it as p, lib.rs:152; advect rewrites it).
+static int op_add_source_diffuse(int b, float*& x, float* x0, float*& scratch, float* z_tmp, const Geom& g, float diff,
+                                 float dt, int iters, int fused, cudaStream_t st) {
+    const float a = ((dt * diff) * (float)g.nx) * (float)g.ny;
+    const float c = 1.0f + 4.0f * a;
+    if (degenerate(g) || resolve_fused(g, iters, fused) <= 1 || !z_tmp) {
+        TRY(op_add_source(x0, x, nullptr, nullptr, g, dt, st));
+        return op_lin_solve(b, x, x0, scratch, g, a, c, iters, fused, st);
+    }
+    return op_lin_solve(b, x, x0, scratch, g, a, c, iters, fused, st, false, true, dt, z_tmp);
 }
 
 // advect, src/lib.rs:84-126, for 1 or 2 fields sharing the back-trace.
@@ -234,11 +252,10 @@ static int op_project(float* u, float* v, float*& p, float* div, float*& scratch
 
 // vel_step, src/lib.rs:181-208 (argument roles alternate exactly as in the reference;
 // no SWAPs -- lib.rs:193,196,201-202 are commented out there).
-static int op_vel_step(float*& u, float*& v, float*& u0, float*& v0, float*& s, const Geom& g, float visc, float dt,
-                       int iters, int fused, cudaStream_t st) {
-    TRY(op_add_source(u, u0, v, v0, g, dt, st));                            // lib.rs:190-191
-    TRY(op_diffuse(B_NEGX, u0, u, s, g, visc, dt, iters, fused, st));       // lib.rs:194
-    TRY(op_diffuse(B_NEGY, v0, v, s, g, visc, dt, iters, fused, st));       // lib.rs:197
+static int op_vel_step(float*& u, float*& v, float*& u0, float*& v0, float*& s, float* s2, const Geom& g, float visc,
+                       float dt, int iters, int fused, cudaStream_t st) {
+    TRY(op_add_source_diffuse(B_NEGX, u0, u, s, s2, g, visc, dt, iters, fused, st));  // lib.rs:190,194
+    TRY(op_add_source_diffuse(B_NEGY, v0, v, s, s2, g, visc, dt, iters, fused, st));  // lib.rs:191,197
     TRY(op_project(u0, v0, u, v, s, g, iters, fused, st));                  // lib.rs:199
     float* d[2] = {u, v};
     const float* d0[2] = {u0, v0};
@@ -248,10 +265,9 @@ static int op_vel_step(float*& u, float*& v, float*& u0, float*& v0, float*& s, 
 }
 
 // dens_step, src/lib.rs:171-179.
-static int op_dens_step(float*& x, float*& x0, const float* u, const float* v, float*& s, const Geom& g, float diff,
-                        float dt, int iters, int fused, cudaStream_t st) {
-    TRY(op_add_source(x, x0, nullptr, nullptr, g, dt, st));                 // lib.rs:172
-    TRY(op_diffuse(B_POSITIVE, x0, x, s, g, diff, dt, iters, fused, st));   // lib.rs:175
+static int op_dens_step(float*& x, float*& x0, const float* u, const float* v, float*& s, float* s2, const Geom& g,
+                        float diff, float dt, int iters, int fused, cudaStream_t st) {
+    TRY(op_add_source_diffuse(B_POSITIVE, x0, x, s, s2, g, diff, dt, iters, fused, st));  // lib.rs:172,175
     float* d[1] = {x};
     const float* d0[1] = {x0};
     const int b[1] = {B_POSITIVE};
@@ -263,8 +279,9 @@ static int op_dens_step(float*& x, float*& x0, const float* u, const float* v, f
 // --------------------------------------------------------------------------------------
 struct FieldSet {
     Geom g{};
-    int n = 0;
-    float* buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int n = 0;       // buffers allocated: user fields, then scratch (lib.rs:213,252), then the add_source temporary
+    int n_user = 0;  // fields the crate API exposes
+    float* buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev = nullptr;
     int iters = 20;  // src/lib.rs:52
@@ -277,6 +294,7 @@ struct FieldSet {
         CU(cudaGetDevice(&device));
         g = make_geom(w, h, pitch_for(w));
         n = nfields;
+        n_user = nfields - 2;
         CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         const size_t bytes = g.pitch * h * sizeof(float);
@@ -288,26 +306,26 @@ struct FieldSet {
     }
     void release() {
         if (stream) cudaStreamSynchronize(stream);
-        for (int i = 0; i < 5; ++i) if (buf[i]) cudaFree(buf[i]);
+        for (int i = 0; i < 6; ++i) if (buf[i]) cudaFree(buf[i]);
         if (ev) cudaEventDestroy(ev);
         if (stream) cudaStreamDestroy(stream);
     }
     int upload(int field, const float* host) {
-        if (field < 0 || field >= n - 1 || !host) return fail(FRUID_ERR_BAD_ARG, "bad field %d or null host pointer", field);
+        if (field < 0 || field >= n_user || !host) return fail(FRUID_ERR_BAD_ARG, "bad field %d or null host pointer", field);
         CU(cudaMemcpy2DAsync(buf[field], g.pitch * sizeof(float), host, (size_t)g.w * sizeof(float),
                              (size_t)g.w * sizeof(float), (size_t)g.h, cudaMemcpyHostToDevice, stream));
         CU(cudaStreamSynchronize(stream));  // host buffer may be pageable and reused by the caller
         return 0;
     }
     int download(int field, float* host) {
-        if (field < 0 || field >= n || !host) return fail(FRUID_ERR_BAD_ARG, "bad field %d or null host pointer", field);
+        if (field < 0 || field >= n_user || !host) return fail(FRUID_ERR_BAD_ARG, "bad field %d or null host pointer", field);
         CU(cudaMemcpy2DAsync(host, (size_t)g.w * sizeof(float), buf[field], g.pitch * sizeof(float),
                              (size_t)g.w * sizeof(float), (size_t)g.h, cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
         return 0;
     }
     int inject(int field, size_t x, size_t y, float val) {
-        if (field < 0 || field >= n - 1) return fail(FRUID_ERR_BAD_ARG, "bad field %d", field);
+        if (field < 0 || field >= n_user) return fail(FRUID_ERR_BAD_ARG, "bad field %d", field);
         if (x >= (size_t)g.w || y >= (size_t)g.h) return fail(FRUID_ERR_BAD_ARG, "cell (%zu,%zu) outside %dx%d", x, y, g.w, g.h);
         CU(cudaMemcpyAsync(buf[field] + x + y * g.pitch, &val, sizeof(float), cudaMemcpyHostToDevice, stream));
         return 0;
@@ -324,8 +342,8 @@ struct FieldSet {
     }
 };
 
-struct fruid_fluid { FieldSet s; };    // buf: 0=u 1=v 2=u_prev 3=v_prev 4=scratch (lib.rs:247-253)
-struct fruid_density { FieldSet s; };  // buf: 0=dens 1=dens_prev 2=scratch        (lib.rs:210-214)
+struct fruid_fluid { FieldSet s; };    // buf: 0=u 1=v 2=u_prev 3=v_prev 4=scratch (lib.rs:247-253) 5=add_source temporary
+struct fruid_density { FieldSet s; };  // buf: 0=dens 1=dens_prev 2=scratch (lib.rs:210-214) 3=add_source temporary
 
 #define NEED(h) do { if (!(h)) return fail(FRUID_ERR_BAD_ARG, "null handle"); CU(cudaSetDevice((h)->s.device)); } while (0)
 
@@ -334,7 +352,7 @@ extern "C" int fruid_fluid_create(size_t w, size_t h, fruid_fluid_t** out) {
     *out = nullptr;
     fruid_fluid* f = new (std::nothrow) fruid_fluid();
     if (!f) return fail(FRUID_ERR_OOM, "host allocation failed");
-    int r = f->s.init(w, h, 5);
+    int r = f->s.init(w, h, 6);
     if (r) { f->s.release(); delete f; return r; }
     *out = f;
     return 0;
@@ -351,7 +369,6 @@ extern "C" size_t fruid_fluid_height(const fruid_fluid_t* f) { return f ? (size_
 extern "C" int fruid_fluid_upload(fruid_fluid_t* f, int field, const float* host) { NEED(f); return f->s.upload(field, host); }
 extern "C" int fruid_fluid_download(fruid_fluid_t* f, int field, float* host) {
     NEED(f);
-    if (field == 4) return fail(FRUID_ERR_BAD_ARG, "scratch is not observable (lib.rs:252)");
     return f->s.download(field, host);
 }
 extern "C" int fruid_fluid_inject(fruid_fluid_t* f, int field, size_t x, size_t y, float val) { NEED(f); return f->s.inject(field, x, y, val); }
@@ -360,7 +377,7 @@ extern "C" int fruid_fluid_set_fused_sweeps(fruid_fluid_t* f, int t) { NEED(f); 
 extern "C" int fruid_fluid_step(fruid_fluid_t* f, float dt, float visc) {
     NEED(f);
     FieldSet& s = f->s;
-    return op_vel_step(s.buf[0], s.buf[1], s.buf[2], s.buf[3], s.buf[4], s.g, visc, dt, s.iters, s.fused, s.stream);
+    return op_vel_step(s.buf[0], s.buf[1], s.buf[2], s.buf[3], s.buf[4], s.buf[5], s.g, visc, dt, s.iters, s.fused, s.stream);
 }
 extern "C" int fruid_fluid_step_n(fruid_fluid_t* f, float dt, float visc, int n) {
     NEED(f);
@@ -376,7 +393,7 @@ extern "C" int fruid_density_create(size_t w, size_t h, fruid_density_t** out) {
     *out = nullptr;
     fruid_density* d = new (std::nothrow) fruid_density();
     if (!d) return fail(FRUID_ERR_OOM, "host allocation failed");
-    int r = d->s.init(w, h, 3);
+    int r = d->s.init(w, h, 4);
     if (r) { d->s.release(); delete d; return r; }
     *out = d;
     return 0;
@@ -391,7 +408,6 @@ extern "C" int fruid_density_destroy(fruid_density_t* d) {
 extern "C" int fruid_density_upload(fruid_density_t* d, int field, const float* host) { NEED(d); return d->s.upload(field, host); }
 extern "C" int fruid_density_download(fruid_density_t* d, int field, float* host) {
     NEED(d);
-    if (field == 2) return fail(FRUID_ERR_BAD_ARG, "scratch is not observable (lib.rs:213)");
     return d->s.download(field, host);
 }
 extern "C" int fruid_density_inject(fruid_density_t* d, int field, size_t x, size_t y, float val) { NEED(d); return d->s.inject(field, x, y, val); }
@@ -419,7 +435,7 @@ extern "C" int fruid_density_step_dev(fruid_density_t* d, fruid_fluid_t* vel, fl
     // u,v are produced on vel's stream and consumed on ours; order both ways.
     CU(cudaEventRecord(vs.ev, vs.stream));
     CU(cudaStreamWaitEvent(s.stream, vs.ev, 0));
-    TRY(op_dens_step(s.buf[0], s.buf[1], vs.buf[0], vs.buf[1], s.buf[2], s.g, diff, dt, s.iters, s.fused, s.stream));
+    TRY(op_dens_step(s.buf[0], s.buf[1], vs.buf[0], vs.buf[1], s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream));
     CU(cudaEventRecord(s.ev, s.stream));
     CU(cudaStreamWaitEvent(vs.stream, s.ev, 0));
     return 0;
@@ -435,7 +451,7 @@ extern "C" int fruid_density_step_host(fruid_density_t* d, const float* u, const
     const size_t rb = (size_t)s.g.w * sizeof(float);
     CU(cudaMemcpy2DAsync(du, s.g.pitch * sizeof(float), u, rb, rb, (size_t)s.g.h, cudaMemcpyHostToDevice, s.stream));
     CU(cudaMemcpy2DAsync(dv, s.g.pitch * sizeof(float), v, rb, rb, (size_t)s.g.h, cudaMemcpyHostToDevice, s.stream));
-    int r = op_dens_step(s.buf[0], s.buf[1], du, dv, s.buf[2], s.g, diff, dt, s.iters, s.fused, s.stream);
+    int r = op_dens_step(s.buf[0], s.buf[1], du, dv, s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream);
     cudaFreeAsync(du, s.stream);
     cudaFreeAsync(dv, s.stream);
     TRY(r);

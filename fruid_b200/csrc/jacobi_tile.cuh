@@ -57,7 +57,31 @@ struct TileArgs {
     int SX, SY;  // tile strides = extent - 2H
     int ntx, nty;
     int x_is_zero;  // the incoming iterate is identically +0 (pressure solve, lib.rs:152,160): skip its load
+    int* sched;     // [0] = next work item, [1] = CTAs finished (both self-reset by the last CTA)
+    // add_source (lib.rs:5-10) folded into the first block of a diffuse: x0 += dt * x_initial
+    // (the initial iterate of diffuse IS the source field, lib.rs:172-175,190-197).  The updated
+    // right-hand side goes to z_out (a different buffer: other CTAs still read x0 as halo).
+    int fuse_src;
+    float src_dt;
+    float* z_out;
 };
+
+// Work item -> tile.  Tiles touching the domain boundary execute more instructions, so they are
+// handed out first (longest-first keeps the tail of the persistent grid short); interior tiles
+// follow in row-major order so that concurrently running CTAs share halo rows/columns in L2.
+__device__ __forceinline__ void tile_of_item(int item, int ntx, int nty, int& kx, int& ky) {
+    if (ntx < 3 || nty < 3) { kx = item % ntx; ky = item / ntx; return; }
+    if (item < ntx) { kx = item; ky = 0; return; }
+    item -= ntx;
+    if (item < ntx) { kx = item; ky = nty - 1; return; }
+    item -= ntx;
+    if (item < nty - 2) { kx = 0; ky = 1 + item; return; }
+    item -= nty - 2;
+    if (item < nty - 2) { kx = ntx - 1; ky = 1 + item; return; }
+    item -= nty - 2;
+    kx = 1 + item % (ntx - 2);
+    ky = 1 + item / (ntx - 2);
+}
 
 // One float4 row of the update.  t = l + r per component (scalar adds: the operands are
 // not register-pair aligned); the remaining adds and multiplies use the sm_100 packed
@@ -148,7 +172,7 @@ __device__ __forceinline__ float4 jac_row_full(float4 cc, float4 up, float4 dn, 
 
 template <int R, int NW, int MODE, bool EDGE>
 __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int ky, float4 (&v)[R + 1],
-                                                 const float4 (&z)[R], float4* __restrict__ halo) {
+                                                 float4 (&z)[R], float4* __restrict__ halo) {
     constexpr int TH = R * NW;
     constexpr int HB = (NW * 2 + 2) * 32;  // float4 slots per halo buffer (one guard row at each end)
     const unsigned FULL = 0xffffffffu;
@@ -166,6 +190,17 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
     if (EDGE) {
         E.l1 = (gx0 + 1 == 1);  // ox == 0 && lane == 0 (tile origins are multiples of 4)
         E.r0 = (gx0 + 0 == g.w - 2); E.r1 = (gx0 + 1 == g.w - 2); E.r2 = (gx0 + 2 == g.w - 2); E.r3 = (gx0 + 3 == g.w - 2);
+    }
+
+    if (A.fuse_src) {  // add_source: x0[k] = x0[k] + s[k]*dt on every cell (border included)
+        const float dt = A.src_dt;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            z[r].x = fadd(z[r].x, fmul(v[r + 1].x, dt));
+            z[r].y = fadd(z[r].y, fmul(v[r + 1].y, dt));
+            z[r].z = fadd(z[r].z, fmul(v[r + 1].z, dt));
+            z[r].w = fadd(z[r].w, fmul(v[r + 1].w, dt));
+        }
     }
 
     // My top-row slot in halo buffer 0 (+32: my bottom row).  Slot -32 is the bottom row of the
@@ -213,21 +248,57 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
     const bool v0 = gx0 + 0 >= xlo && gx0 + 0 < xhi, v1 = gx0 + 1 >= xlo && gx0 + 1 < xhi;
     const bool v2 = gx0 + 2 >= xlo && gx0 + 2 < xhi, v3 = gx0 + 3 >= xlo && gx0 + 3 < xhi;
     const bool vall = v0 && v1 && v2 && v3;
+    if (!EDGE) {
+        // Interior tile: [xlo, xhi) = [ox+H, ox+128-H) with H even, so a lane stores its whole
+        // float4, its low or high half (8-byte aligned), or nothing -- no per-component tests.
+        const int lo = A.H - 4 * lane, hi = 128 - A.H - 4 * lane;  // my components [lo, hi) are stored
+        const int mode = (lo <= 0 && hi >= 4) ? 1 : (lo <= 0 && hi == 2) ? 2 : (lo == 2 && hi >= 4) ? 3 : 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int gy = gyw + r;
+            if (gy < ylo || gy >= yhi) continue;  // warp-uniform
+            float* row = A.out + (size_t)gy * g.pitch + gx0;
+            if (mode == 1) *reinterpret_cast<float4*>(row) = xr[r];
+            else if (mode == 2) *reinterpret_cast<float2*>(row) = make_float2(xr[r].x, xr[r].y);
+            else if (mode == 3) *reinterpret_cast<float2*>(row + 2) = make_float2(xr[r].z, xr[r].w);
+            if (A.fuse_src && A.z_out) {
+                float* zr = A.z_out + (size_t)gy * g.pitch + gx0;
+                if (mode == 1) *reinterpret_cast<float4*>(zr) = z[r];
+                else if (mode == 2) *reinterpret_cast<float2*>(zr) = make_float2(z[r].x, z[r].y);
+                else if (mode == 3) *reinterpret_cast<float2*>(zr + 2) = make_float2(z[r].z, z[r].w);
+            }
+        }
+        return;
+    }
+    if (A.fuse_src && A.z_out) {  // the updated right-hand side, all rows of my output band (border rows too)
+        const int zlo = (ky == 0) ? 0 : oy + A.H, zhi = lasty ? g.h : oy + TH - A.H;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int gy = gyw + r;
+            if (gy < zlo || gy >= zhi) continue;
+            float* row = A.z_out + (size_t)gy * g.pitch;
+            if (vall) {
+                *reinterpret_cast<float4*>(row + gx0) = z[r];
+            } else {
+                if (v0) row[gx0 + 0] = z[r].x;
+                if (v1) row[gx0 + 1] = z[r].y;
+                if (v2) row[gx0 + 2] = z[r].z;
+                if (v3) row[gx0 + 3] = z[r].w;
+            }
+        }
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int gy = gyw + r;
         if (gy < ylo || gy >= yhi) continue;  // warp-uniform
         float4 f = xr[r];
-        float vleft = 0.f;  // value at gx0-1 (only needed when my .x is the right border column)
-        if (EDGE) {
-            vleft = __shfl_up_sync(FULL, f.w, 1);
-            // column borders of this interior row (lib.rs:31-32)
-            if (gx0 == 0) f.x = sgn(negx, f.y);
-            if (gx0 + 0 == g.w - 1) f.x = sgn(negx, vleft);
-            if (gx0 + 1 == g.w - 1) f.y = sgn(negx, f.x);
-            if (gx0 + 2 == g.w - 1) f.z = sgn(negx, f.y);
-            if (gx0 + 3 == g.w - 1) f.w = sgn(negx, f.z);
-        }
+        // column borders of this interior row (lib.rs:31-32); vleft = value at gx0-1
+        const float vleft = __shfl_up_sync(FULL, f.w, 1);
+        if (gx0 == 0) f.x = sgn(negx, f.y);
+        if (gx0 + 0 == g.w - 1) f.x = sgn(negx, vleft);
+        if (gx0 + 1 == g.w - 1) f.y = sgn(negx, f.x);
+        if (gx0 + 2 == g.w - 1) f.z = sgn(negx, f.y);
+        if (gx0 + 3 == g.w - 1) f.w = sgn(negx, f.z);
         float* row = A.out + (size_t)gy * g.pitch;
         if (vall) {
             *reinterpret_cast<float4*>(row + gx0) = f;
@@ -237,7 +308,7 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
             if (v2) row[gx0 + 2] = f.z;
             if (v3) row[gx0 + 3] = f.w;
         }
-        if (EDGE && (gy == 1 || gy == g.h - 2)) {
+        if (gy == 1 || gy == g.h - 2) {
             // border row(s) mirrored from this row (lib.rs:36-37) and their corners (lib.rs:40-43):
             // corner = 0.5*(row-edge + col-edge) = 0.5*(sy*v + sx*v), v = diagonal interior cell;
             // f already holds sx*v in the border columns.
@@ -264,7 +335,7 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
 template <int R, int NW>
 constexpr size_t jacobi_tile_smem_bytes() {
     // TMA staging of the next tile's x0 and x + halo exchange (2 buffers, NW*2+2 rows of 512 B) + mbarrier
-    return (size_t)2 * R * NW * 512 + (size_t)2 * (NW * 2 + 2) * 512 + 16;
+    return (size_t)2 * R * NW * 512 + (size_t)2 * (NW * 2 + 2) * 512 + 32;
 }
 
 template <int R, int NW, int MODE>
@@ -276,25 +347,33 @@ __global__ void __launch_bounds__(NW * 32, 1) k_jacobi_tile(const __grid_constan
     float* const xs = reinterpret_cast<float*>(smem_raw + (size_t)TILE_BYTES);   // [TH][128] x staging  (TMA dst)
     float4* const halo = reinterpret_cast<float4*>(smem_raw + (size_t)2 * TILE_BYTES);
     uint64_t* const mbar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)2 * TILE_BYTES + (size_t)2 * (NW * 2 + 2) * 512);
+    volatile int* const s_item = reinterpret_cast<volatile int*>(mbar + 1);       // [2]: item of this / the next tile
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const int ntiles = A.ntx * A.nty;
     const uint32_t tx_bytes = A.x_is_zero ? TILE_BYTES : 2 * TILE_BYTES;
 
-    int tile = blockIdx.x;
     if (threadIdx.x == 0) {
         mbar_init(mbar, 1);
-        if (tile < ntiles) {
-            const int kx = tile % A.ntx, ky = tile / A.ntx;
+        const int item = atomicAdd(&A.sched[0], 1);
+        s_item[0] = item;
+        if (item < ntiles) {
+            int kx, ky;
+            tile_of_item(item, A.ntx, A.nty, kx, ky);
             mbar_expect_tx(mbar, tx_bytes);
             tma_load_2d(zs, &A.tm_x0, kx * A.SX, ky * A.SY, mbar);
             if (!A.x_is_zero) tma_load_2d(xs, &A.tm_x, kx * A.SX, ky * A.SY, mbar);
         }
     }
-    __syncthreads();  // barrier init visible to every waiter
+    __syncthreads();  // barrier init + first work item visible to every thread
 
     uint32_t phase = 0;
-    for (; tile < ntiles; tile += gridDim.x) {
-        const int kx = tile % A.ntx, ky = tile / A.ntx;
+    int slot = 0;
+    for (int item = s_item[0]; item < ntiles; item = s_item[slot]) {
+        int kx, ky;
+        tile_of_item(item, A.ntx, A.nty, kx, ky);
+        // Claim the next work item now: the atomic's round trip hides behind the wait + copy below.
+        int next = 0;
+        if (threadIdx.x == 0) next = atomicAdd(&A.sched[0], 1);
         mbar_wait(mbar, phase);  // this tile's x0 (and x) have landed in the staging buffers
         phase ^= 1u;
 
@@ -311,13 +390,17 @@ __global__ void __launch_bounds__(NW * 32, 1) k_jacobi_tile(const __grid_constan
             v[0] = v[1];
         }
         __syncthreads();  // staging buffers are free again (and the previous tile's halo reads are done)
-        const int next = tile + gridDim.x;
-        if (threadIdx.x == 0 && next < ntiles) {  // prefetch the next tile behind this tile's sweeps
-            const int nkx = next % A.ntx, nky = next / A.ntx;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before async writes
-            mbar_expect_tx(mbar, tx_bytes);
-            tma_load_2d(zs, &A.tm_x0, nkx * A.SX, nky * A.SY, mbar);
-            if (!A.x_is_zero) tma_load_2d(xs, &A.tm_x, nkx * A.SX, nky * A.SY, mbar);
+        slot ^= 1;
+        if (threadIdx.x == 0) {  // prefetch the next tile behind this tile's sweeps
+            s_item[slot] = next;  // read by everyone after the sweeps' barriers
+            if (next < ntiles) {
+                int nkx, nky;
+                tile_of_item(next, A.ntx, A.nty, nkx, nky);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before async writes
+                mbar_expect_tx(mbar, tx_bytes);
+                tma_load_2d(zs, &A.tm_x0, nkx * A.SX, nky * A.SY, mbar);
+                if (!A.x_is_zero) tma_load_2d(xs, &A.tm_x, nkx * A.SX, nky * A.SY, mbar);
+            }
         }
         const int ox = kx * A.SX, oy = ky * A.SY;
         const bool edge = (kx == 0) || (ky == 0) || (ox + 128 >= A.g.w - 1) || (oy + TH >= A.g.h - 1);
@@ -325,6 +408,15 @@ __global__ void __launch_bounds__(NW * 32, 1) k_jacobi_tile(const __grid_constan
             jacobi_tile_body<R, NW, MODE, true>(A, kx, ky, v, z, halo);
         else
             jacobi_tile_body<R, NW, MODE, false>(A, kx, ky, v, z, halo);
+    }
+    // The last CTA to leave resets the scheduler for the next launch on this stream.
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&A.sched[1], 1) == (int)gridDim.x - 1) {
+            A.sched[0] = 0;
+            A.sched[1] = 0;
+            __threadfence();
+        }
     }
 }
 
@@ -385,6 +477,20 @@ static int tile_tensor_map(const float* base, size_t pitch, int h, int th, CUten
     return 0;
 }
 
+// Per-stream scheduler words (zeroed once; every launch leaves them zero again).
+static std::mutex g_sched_mu;
+static std::unordered_map<cudaStream_t, int*> g_sched;
+static int* tile_sched_for(cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_sched_mu);
+    auto it = g_sched.find(st);
+    if (it != g_sched.end()) return it->second;
+    int* p = nullptr;
+    if (cudaMalloc(&p, 2 * sizeof(int)) != cudaSuccess) return nullptr;
+    if (cudaMemset(p, 0, 2 * sizeof(int)) != cudaSuccess) { cudaFree(p); return nullptr; }
+    g_sched.emplace(st, p);
+    return p;
+}
+
 static inline int jacobi_tile_max_T(int R, int NW) {
     const int th = R * NW;
     int H = (th < 128 ? th : 128) / 2 - 2;  // keep at least 4 output rows/cols per tile
@@ -438,13 +544,16 @@ static inline int tiles_needed(int extent, int tile, int stride) {
 
 // Returns 0 or a negative fruid_status (-7 = bad argument, -4 = CUDA error).
 static int jacobi_tile_launch(float* out, const float* x, const float* x0, const Geom& g, float a, float c, int b, int T,
-                              int x_is_zero, cudaStream_t st) {
+                              int x_is_zero, cudaStream_t st, int fuse_src = 0, float src_dt = 0.f, float* z_out = nullptr) {
     const int R = g_tile_cfg.R, NW = g_tile_cfg.NW, TH = R * NW;
     if (T < 1 || T > jacobi_tile_max_T(R, NW)) return -7;
     TileArgs A;
     if (int r = tile_tensor_map(x0, g.pitch, g.h, TH, &A.tm_x0)) return r;
     if (int r = tile_tensor_map(x, g.pitch, g.h, TH, &A.tm_x)) return r;
     A.out = out; A.x = x; A.g = g; A.a = a; A.b = b; A.T = T; A.x_is_zero = x_is_zero;
+    A.fuse_src = fuse_src; A.src_dt = src_dt; A.z_out = z_out;
+    A.sched = tile_sched_for(st);
+    if (!A.sched) return -4;
     A.H = T + (T & 1);
     A.SX = 128 - 2 * A.H;
     A.SY = TH - 2 * A.H;
