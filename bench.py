@@ -360,7 +360,99 @@ def run_e2e(args, fb, torch, sc, w, h):
 
 
 def run_b200_multi(args, fb, dist, rank, world, local):
-    raise SystemExit("multi-GPU slab path not built yet")
+    """N GPUs of one node, one process per GPU: the scene is y-slab decomposed (rank r owns rows
+    [r*h/N, (r+1)*h/N) plus 12 halo rows of each neighbour); halo rows and advection gathers move
+    over NVLink peer memory inside the library's kernels.  WEAK scaling: w x (w*N) cells, i.e. the
+    single-GPU workload per GPU.  Time = max over ranks of the CUDA-event time of the K steps,
+    bracketed by barriers."""
+    import torch
+    from fruid_b200 import _lib
+    from fruid_b200.dist import SlabDensitySim, SlabFluidSim
+    L = _lib.lib
+    w = args.size
+    h = args.rows if args.rows else args.size * world
+    sim = SlabFluidSim(w, h, rank, world)
+    den = SlabDensitySim(w, h, rank, world)
+    sc = make_scene(w, h, sim.y0, sim.y1)
+    for name, field in (("u", 0), ("v", 1), ("u_prev", 2), ("v_prev", 3)):
+        sim.upload(field, sc[name])
+    for name, field in (("dens", 0), ("dens_prev", 1)):
+        den.upload(field, sc[name])
+    stream = torch.cuda.ExternalStream(int(L.fruid_fluid_stream(sim._h)))
+
+    def scene_step():
+        sim.step(DT, VISC)
+        den.step(sim, DT, DIFF)
+
+    for _ in range(args.warmup):
+        scene_step()
+    sim.sync(); den.sync()
+    torch.cuda.synchronize()
+    dist.barrier()
+    n0 = fb.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(args.steps):
+            scene_step()
+        e1.record(stream)
+        sim.sync(); den.sync()
+        torch.cuda.synchronize()
+    dist.barrier()
+    launches = fb.launch_count() - n0
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    value = w * h * args.steps / (ms * 1e-3)
+
+    # end to end: every step each rank uploads its rows of the three source fields and downloads
+    # its rows of the density (host <-> device inside the timed region), wall clock, max over ranks
+    rows = sim.y1 - sim.y0
+    host = {k: np.ascontiguousarray(sc[k]) for k in ("u_prev", "v_prev", "dens_prev")}
+    out = np.empty((rows, w), np.float32)
+    pinned = [a for a in (*host.values(), out) if L.fruid_host_register(a.ctypes.data, a.nbytes) == 0]
+
+    def e2e_step():
+        sim.upload(_lib.U_PREV, host["u_prev"])
+        sim.upload(_lib.V_PREV, host["v_prev"])
+        den.upload(_lib.DENS_PREV, host["dens_prev"])
+        scene_step()
+        _lib.check(L.fruid_density_download(den._h, _lib.DENS, _lib.ptr(out)))
+
+    e2e_step()
+    torch.cuda.synchronize(); dist.barrier()
+    n = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        e2e_step()
+    torch.cuda.synchronize(); dist.barrier()
+    sec = torch.tensor([time.perf_counter() - t0], device="cuda")
+    dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+    for a in pinned:
+        L.fruid_host_unregister(a.ctypes.data)
+    e2e = {"value": w * h * n / float(sec.item()), "unit": "cell-steps/s", "h2d_bytes_per_step": 3 * w * h * 4,
+           "d2h_bytes_per_step": w * h * 4, "steps": n,
+           "note": "whole-job bytes; each rank moves its own rows (h2d of 3 source fields, d2h of density) every step"}
+
+    if rank == 0:
+        cfg = workload_config(args, world)
+        cfg["workload"] = (f"{w}x{h} scene step y-slab decomposed over {world} GPUs ({w}x{h // world} cells per GPU, weak "
+                           f"scaling of the {w}x{w} single-GPU workload); FluidSim::step + 1x DensitySim::step, K={ITERS}")
+        cfg["grid"] = [w, h]
+        cfg["halo_rows"] = 12
+        line = {"metric": "cell-steps/sec", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak" if not args.rows else "custom", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": cfg, "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": bytes_per_cell_step() * value / world / 1e9,
+                             "peak": 6551.4, "unit": "GB/s", "frac": bytes_per_cell_step() * value / world / 1e9 / 6551.4,
+                             "traffic": None, "note": "per-GPU algorithmic bytes (188+60K per cell-step) / time; see the "
+                                                      "N=1 line for the dominant kernel"},
+                "cpu_baseline": None, "impl": "b200"}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def main():
@@ -371,6 +463,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--fused", type=int, default=None, help="Jacobi sweeps per launch (default: library choice)")
+    ap.add_argument("--rows", type=int, default=0, help="multi-GPU: global rows (default size*N = weak scaling)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

@@ -49,6 +49,13 @@ SIGNATURES = {
     "fruid_fluid_stream": [_vp],
     "fruid_density_stream": [_vp],
     "fruid_fluid_create": [_sz, _sz, ctypes.POINTER(_vp)],
+    "fruid_fluid_create_slab": [_sz, _sz, _i, _i, ctypes.POINTER(_vp)],
+    "fruid_fluid_ipc_export": [_vp, _vp],
+    "fruid_fluid_ipc_attach": [_vp, _i, _vp],
+    "fruid_fluid_slab_rows": [_vp, ctypes.POINTER(_sz), ctypes.POINTER(_sz)],
+    "fruid_density_create_slab": [_sz, _sz, _i, _i, ctypes.POINTER(_vp)],
+    "fruid_density_ipc_export": [_vp, _vp],
+    "fruid_density_ipc_attach": [_vp, _i, _vp],
     "fruid_fluid_destroy": [_vp],
     "fruid_fluid_width": [_vp],
     "fruid_fluid_height": [_vp],

@@ -37,7 +37,7 @@ class Array2D:
         self._cells = []      # pending single-cell writes (x, y, value)
 
     def __del__(self):
-        if getattr(self, "_pinned", False):
+        if getattr(self, "_pinned", False) and lib is not None:
             self._pinned = False
             lib.fruid_host_unregister(self._host.ctypes.data)
 
@@ -129,7 +129,7 @@ class FluidSim:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:
             lib.fruid_fluid_destroy(h)
 
     # transfers used by the mirrors
@@ -186,7 +186,7 @@ class DensitySim:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:
             lib.fruid_density_destroy(h)
 
     def _download(self, field, host):

@@ -19,16 +19,28 @@ __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b)
 
 enum : int { B_POSITIVE = 0, B_NEGX = 1, B_NEGY = 2 };  // enum Bounds, src/lib.rs:19-25
 
-// Grid geometry: w x h cells including the border, rows of `pitch` floats.
+// Grid geometry.  The global field is w x gh cells including the border (the constructor
+// arguments of FluidSim::new); this device holds `h` consecutive rows of it starting at global
+// row gy0 (a y-slab: owned rows plus halo rows of the neighbours).  Single GPU: gy0 = 0, h = gh.
+// Rows are addressed LOCALLY (row ly at ly*pitch); boundary logic uses the GLOBAL row ly + gy0.
 struct Geom {
-    int w, h;       // total size (constructor arguments of FluidSim::new)
-    int nx, ny;     // interior size, src/lib.rs:12-17
+    int w, h;       // columns; LOCAL rows held by this device
+    int nx, ny;     // GLOBAL interior size (w-2, gh-2), src/lib.rs:12-17
     size_t pitch;   // floats per device row (multiple of 32 for library-owned fields)
+    int gy0;        // global row of local row 0
+    int gh;         // global number of rows
 };
 
 __host__ __device__ __forceinline__ Geom make_geom(size_t w, size_t h, size_t pitch) {
     Geom g;
     g.w = (int)w; g.h = (int)h; g.nx = (int)w - 2; g.ny = (int)h - 2; g.pitch = pitch;
+    g.gy0 = 0; g.gh = (int)h;
+    return g;
+}
+__host__ __device__ __forceinline__ Geom make_slab_geom(size_t w, size_t gh, size_t pitch, int gy0, int h_local) {
+    Geom g;
+    g.w = (int)w; g.h = h_local; g.nx = (int)w - 2; g.ny = (int)gh - 2; g.pitch = pitch;
+    g.gy0 = gy0; g.gh = (int)gh;
     return g;
 }
 

@@ -4,7 +4,10 @@
 // every entry point either runs the CUDA kernels or returns an error.
 #include "../../include/fruid_b200.h"
 
+#include <algorithm>
 #include <atomic>
+#include <functional>
+#include <initializer_list>
 #include <cstdarg>
 #include <cstdio>
 #include <cmath>
@@ -18,6 +21,7 @@
 #include "kernels_serial.cuh"
 #include "kernels_vec.cuh"
 #include "jacobi_tile.cuh"
+#include "slab_comm.cuh"
 
 using namespace fruid;
 
@@ -123,12 +127,12 @@ extern "C" const char* fruid_build_info(void) { return "fruid_b200 0.1 (sm_100a,
 // operator launchers on device buffers
 // --------------------------------------------------------------------------------------
 static inline size_t pitch_for(size_t w) { return (w + 31) / 32 * 32; }
-static inline bool degenerate(const Geom& g) { return g.nx < 1 || g.ny < 1; }
+static inline bool degenerate(const Geom& g) { return g.nx < 1 || g.ny < 1; }  // empty interior (w == 2 or h == 2)
 static inline dim3 cell_block() { return dim3(128, 2); }
 static inline dim3 cell_grid(int cx, int cy) { return dim3((cx + 127) / 128, (cy + 1) / 2); }
 // float4-per-thread kernels: a warp covers 128 columns of one interior row
 static inline dim3 vec_block() { return dim3(32, 8); }
-static inline dim3 vec_grid(const Geom& g) { return dim3(((g.w + 3) / 4 + 31) / 32, (g.ny + 7) / 8); }
+static inline dim3 vec_grid(const Geom& g) { return dim3(((g.w + 3) / 4 + 31) / 32, (g.h - 2 + 7) / 8); }
 
 static int op_add_source(float* x1, const float* s1, float* x2, const float* s2, const Geom& g, float dt,
                          cudaStream_t st) {
@@ -157,7 +161,8 @@ static inline int resolve_fused(const Geom& g, int iters, int fused) {
 }
 static int op_lin_solve(int b, float*& x, const float* x0, float*& scratch, const Geom& g, float a, float c,
                         int iters, int fused, cudaStream_t st, bool x_is_zero = false, bool fuse_src = false,
-                        float src_dt = 0.f, float* z_tmp = nullptr) {
+                        float src_dt = 0.f, float* z_tmp = nullptr,
+                        const std::function<int(float*)>* between_blocks = nullptr) {
     if (iters < 2 || (iters & 1)) return fail(FRUID_ERR_ODD_ITERATIONS, "iterations must be even and >= 2, got %d", iters);
     if (degenerate(g)) {
         LAUNCH("k_serial_lin_solve", st, k_serial_lin_solve<<<1, 1, 0, st>>>(x, x0, scratch, g, a, c, b, iters));
@@ -183,6 +188,9 @@ static int op_lin_solve(int b, float*& x, const float* x0, float*& scratch, cons
         TRY(launched("k_jacobi_tile", st));
         done += T;
         float* t = x; x = scratch; scratch = t;
+        // slab mode: the new iterate is valid SLAB_HALO - T rows beyond the owned rows; refresh
+        // the halo rows from the neighbours before the next block consumes them
+        if (between_blocks && k + 1 < nblocks) TRY((*between_blocks)(x));
     }
     return 0;
 }
@@ -210,9 +218,11 @@ static int op_add_source_diffuse(int b, float*& x, float* x0, float*& scratch, f
     return op_lin_solve(b, x, x0, scratch, g, a, c, iters, fused, st, false, true, dt, z_tmp);
 }
 
-// advect, src/lib.rs:84-126, for 1 or 2 fields sharing the back-trace.
+// advect, src/lib.rs:84-126, for 1 or 2 fields sharing the back-trace.  `tab` (optional) says where
+// the rows of the gathered fields live when they are slab-decomposed; [ly0, ly1) are the local
+// rows to produce (default: every interior row).
 static int op_advect(int nf, float* const* d, const float* const* d0, const int* b, const float* u, const float* v,
-                     const Geom& g, float dt, cudaStream_t st) {
+                     const Geom& g, float dt, cudaStream_t st, const SlabTable* tab = nullptr, int ly0 = -1, int ly1 = -1) {
     const float dt0 = dt * (float)g.nx, dt1 = dt * (float)g.ny;
     const float xmax = (float)g.nx + 0.5f, ymax = (float)g.ny + 0.5f;
     if (degenerate(g)) {
@@ -224,10 +234,21 @@ static int op_advect(int nf, float* const* d, const float* const* d0, const int*
     }
     AdvectArgs a{};
     for (int f = 0; f < nf; ++f) { a.d[f] = d[f]; a.d0[f] = d0[f]; a.b[f] = b[f]; }
-    if (nf == 2)
-        LAUNCH("k_advect4x2", st, k_advect4<2><<<vec_grid(g), vec_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax));
+    SlabTable single{};
+    single.world = 1;
+    const bool multi = tab && tab->world > 1;
+    if (!multi) tab = &single;
+    if (ly0 < 0) { ly0 = 1; ly1 = g.h - 1; }
+    if (ly1 <= ly0) return 0;
+    const dim3 grid(((g.w + 3) / 4 + 31) / 32, (ly1 - ly0 + 7) / 8);
+    if (nf == 2 && multi)
+        LAUNCH("k_advect4x2", st, (k_advect4<2, true><<<grid, vec_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, *tab)));
+    else if (nf == 2)
+        LAUNCH("k_advect4x2", st, (k_advect4<2, false><<<grid, vec_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, *tab)));
+    else if (multi)
+        LAUNCH("k_advect4x1", st, (k_advect4<1, true><<<grid, vec_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, *tab)));
     else
-        LAUNCH("k_advect4x1", st, k_advect4<1><<<vec_grid(g), vec_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax));
+        LAUNCH("k_advect4x1", st, (k_advect4<1, false><<<grid, vec_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, *tab)));
     return 0;
 }
 
@@ -277,57 +298,103 @@ static int op_dens_step(float*& x, float*& x0, const float* u, const float* v, f
 // --------------------------------------------------------------------------------------
 // handles
 // --------------------------------------------------------------------------------------
+// Slab decomposition state of a handle (world == 1: plain single-GPU handle).
+struct SlabInfo {
+    int rank = 0, world = 1;
+    int own0[SLAB_MAX_RANKS + 1] = {0};  // owned global rows of rank r: [own0[r], own0[r+1])
+    int row0[SLAB_MAX_RANKS] = {0};      // global row of local row 0 of rank r
+    int rows[SLAB_MAX_RANKS] = {0};      // local rows of rank r
+    char* peer_base[SLAB_MAX_RANKS] = {nullptr};  // every rank's allocation as mapped here ([rank] = mine)
+    int attached = 1;                    // how many of them are mapped (mine counts)
+    int ev_pull = 0, ev_bar = 0;         // epochs of the last exchange / barrier
+};
+
 struct FieldSet {
     Geom g{};
     int n = 0;       // buffers allocated: user fields, then scratch (lib.rs:213,252), then the add_source temporary
     int n_user = 0;  // fields the crate API exposes
     float* buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    char* base = nullptr;  // the one device allocation: [flag block][field 0][field 1]...
+    size_t field_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev = nullptr;
     int iters = 20;  // src/lib.rs:52
     int fused = 0;   // 0 = library default
     int device = 0;
+    SlabInfo slab;
 
-    int init(size_t w, size_t h, int nfields) {
-        if (w < 2 || h < 2) return fail(FRUID_ERR_BAD_SIZE, "grid must be at least 2x2 (got %zux%zu)", w, h);
-        if (w > (size_t)1 << 20 || h > (size_t)1 << 20) return fail(FRUID_ERR_BAD_SIZE, "grid too large (%zux%zu)", w, h);
+    bool is_slab() const { return slab.world > 1; }
+    // local rows [lo, hi) that this rank owns
+    int own_lo() const { return slab.own0[slab.rank] - slab.row0[slab.rank]; }
+    int own_hi() const { return slab.own0[slab.rank + 1] - slab.row0[slab.rank]; }
+    size_t peer_field_bytes(int r) const { return g.pitch * (size_t)slab.rows[r] * sizeof(float); }
+    int phys_index(const float* p) const { return (int)(((const char*)p - (base + SLAB_FLAG_BYTES)) / field_bytes); }
+    float* peer_field(int r, int phys) const { return (float*)(slab.peer_base[r] + SLAB_FLAG_BYTES + (size_t)phys * peer_field_bytes(r)); }
+    SlabFlags* flags(int r) const { return (SlabFlags*)slab.peer_base[r]; }
+
+    int init(size_t w, size_t gh, int nfields, int rank = 0, int world = 1) {
+        if (w < 2 || gh < 2) return fail(FRUID_ERR_BAD_SIZE, "grid must be at least 2x2 (got %zux%zu)", w, gh);
+        if (w > (size_t)1 << 20 || gh > (size_t)1 << 20) return fail(FRUID_ERR_BAD_SIZE, "grid too large (%zux%zu)", w, gh);
+        if (world < 1 || world > SLAB_MAX_RANKS || rank < 0 || rank >= world)
+            return fail(FRUID_ERR_BAD_ARG, "bad rank %d / world %d (at most %d ranks)", rank, world, SLAB_MAX_RANKS);
         CU(cudaGetDevice(&device));
-        g = make_geom(w, h, pitch_for(w));
+        slab.rank = rank; slab.world = world;
+        const int per = (int)gh / world;
+        if (world > 1 && (per < 2 * SLAB_HALO || w < 3))
+            return fail(FRUID_ERR_BAD_SIZE, "slab decomposition needs at least %d rows per rank (got %d)", 2 * SLAB_HALO, per);
+        for (int r = 0; r < world; ++r) slab.own0[r] = r * per;
+        slab.own0[world] = (int)gh;
+        for (int r = 0; r < world; ++r) {
+            const int lo = world > 1 ? std::max(0, slab.own0[r] - SLAB_HALO) : 0;
+            const int hi = world > 1 ? std::min((int)gh, slab.own0[r + 1] + SLAB_HALO) : (int)gh;
+            slab.row0[r] = lo;
+            slab.rows[r] = hi - lo;
+        }
+        g = make_slab_geom(w, gh, pitch_for(w), slab.row0[rank], slab.rows[rank]);
         n = nfields;
         n_user = nfields - 2;
         CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        const size_t bytes = g.pitch * h * sizeof(float);
-        for (int i = 0; i < n; ++i) {
-            CU(cudaMalloc(&buf[i], bytes));
-            CU(cudaMemsetAsync(buf[i], 0, bytes, stream));  // Array2D::new zero-fills, lib.rs:218,257
-        }
+        field_bytes = g.pitch * (size_t)g.h * sizeof(float);
+        const size_t total = SLAB_FLAG_BYTES + (size_t)n * field_bytes;
+        CU(cudaMalloc(&base, total));
+        CU(cudaMemsetAsync(base, 0, total, stream));  // Array2D::new zero-fills, lib.rs:218,257
+        for (int i = 0; i < n; ++i) buf[i] = (float*)(base + SLAB_FLAG_BYTES + (size_t)i * field_bytes);
+        slab.peer_base[rank] = base;
+        CU(cudaStreamSynchronize(stream));
         return 0;
     }
     void release() {
         if (stream) cudaStreamSynchronize(stream);
-        for (int i = 0; i < 6; ++i) if (buf[i]) cudaFree(buf[i]);
+        for (int r = 0; r < slab.world; ++r)
+            if (r != slab.rank && slab.peer_base[r]) cudaIpcCloseMemHandle(slab.peer_base[r]);
+        if (base) cudaFree(base);
         if (ev) cudaEventDestroy(ev);
         if (stream) cudaStreamDestroy(stream);
     }
+    // Host arrays cover the rows this rank OWNS (the whole field on one GPU), dense w floats per row.
     int upload(int field, const float* host) {
         if (field < 0 || field >= n_user || !host) return fail(FRUID_ERR_BAD_ARG, "bad field %d or null host pointer", field);
-        CU(cudaMemcpy2DAsync(buf[field], g.pitch * sizeof(float), host, (size_t)g.w * sizeof(float),
-                             (size_t)g.w * sizeof(float), (size_t)g.h, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpy2DAsync(buf[field] + (size_t)own_lo() * g.pitch, g.pitch * sizeof(float), host, (size_t)g.w * sizeof(float),
+                             (size_t)g.w * sizeof(float), (size_t)(own_hi() - own_lo()), cudaMemcpyHostToDevice, stream));
         CU(cudaStreamSynchronize(stream));  // host buffer may be pageable and reused by the caller
         return 0;
     }
     int download(int field, float* host) {
         if (field < 0 || field >= n_user || !host) return fail(FRUID_ERR_BAD_ARG, "bad field %d or null host pointer", field);
-        CU(cudaMemcpy2DAsync(host, (size_t)g.w * sizeof(float), buf[field], g.pitch * sizeof(float),
-                             (size_t)g.w * sizeof(float), (size_t)g.h, cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpy2DAsync(host, (size_t)g.w * sizeof(float), buf[field] + (size_t)own_lo() * g.pitch, g.pitch * sizeof(float),
+                             (size_t)g.w * sizeof(float), (size_t)(own_hi() - own_lo()), cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
-        return 0;
+        return check_peer_error();
     }
+    // (x, y) are GLOBAL cell coordinates; ranks that do not own row y ignore the write (their
+    // halo copy is refreshed from the owner at the start of the next step).
     int inject(int field, size_t x, size_t y, float val) {
         if (field < 0 || field >= n_user) return fail(FRUID_ERR_BAD_ARG, "bad field %d", field);
-        if (x >= (size_t)g.w || y >= (size_t)g.h) return fail(FRUID_ERR_BAD_ARG, "cell (%zu,%zu) outside %dx%d", x, y, g.w, g.h);
-        CU(cudaMemcpyAsync(buf[field] + x + y * g.pitch, &val, sizeof(float), cudaMemcpyHostToDevice, stream));
+        if (x >= (size_t)g.w || y >= (size_t)g.gh) return fail(FRUID_ERR_BAD_ARG, "cell (%zu,%zu) outside %dx%d", x, y, g.w, g.gh);
+        const int ly = (int)y - g.gy0;
+        if (ly < own_lo() || ly >= own_hi()) return 0;
+        CU(cudaMemcpyAsync(buf[field] + x + (size_t)ly * g.pitch, &val, sizeof(float), cudaMemcpyHostToDevice, stream));
         return 0;
     }
     int set_iters(int k) {
@@ -337,13 +404,168 @@ struct FieldSet {
     }
     int set_fused(int t) {
         if (t < 0 || (t > 1 && (t & 1))) return fail(FRUID_ERR_BAD_ARG, "fused sweeps must be 0 (default), 1 or even, got %d", t);
+        if (is_slab() && (t == 1 || t > SLAB_MAX_T)) return fail(FRUID_ERR_BAD_ARG, "slab mode needs 2..%d fused sweeps, got %d", SLAB_MAX_T, t);
         fused = t;
         return 0;
+    }
+    int slab_fused() const {  // fused depth used in slab mode
+        int t = resolve_fused(g, iters, fused);
+        if (t > SLAB_MAX_T) t = SLAB_MAX_T;
+        return t < 2 ? 2 : t;
+    }
+    int check_peer_error() {
+        if (!is_slab()) return 0;
+        int err = 0;
+        CU(cudaMemcpy(&err, &flags(slab.rank)->error, sizeof(int), cudaMemcpyDeviceToHost));
+        if (err) return fail(FRUID_ERR_NO_PEER, "rank %d timed out waiting for a peer (halo exchange / barrier)", slab.rank);
+        return 0;
+    }
+    int need_peers() const {
+        if (is_slab() && slab.attached < slab.world)
+            return fail(FRUID_ERR_NO_PEER, "slab handle: %d of %d peers attached (fruid_*_ipc_attach)", slab.attached, slab.world);
+        return 0;
+    }
+    int ipc_export(void* out64) {
+        if (!out64) return fail(FRUID_ERR_BAD_ARG, "null handle buffer");
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, base));
+        memcpy(out64, &h, 64);
+        return 0;
+    }
+    int ipc_attach(int peer, const void* in64) {
+        if (!in64 || peer < 0 || peer >= slab.world) return fail(FRUID_ERR_BAD_ARG, "bad peer rank %d", peer);
+        if (peer == slab.rank || slab.peer_base[peer]) return 0;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, in64, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(FRUID_ERR_NO_PEER, "cudaIpcOpenMemHandle(rank %d) failed: %s", peer, cudaGetErrorString(e));
+        slab.peer_base[peer] = (char*)p;
+        slab.attached += 1;
+        return 0;
+    }
+    // Halo exchange of up to 4 fields: pull SLAB_HALO rows from each neighbour's owned rows.
+    int exchange(std::initializer_list<float*> fields) {
+        if (!is_slab()) return 0;
+        PullArgs A{};
+        const int me = slab.rank;
+        A.me = me; A.pitch = g.pitch; A.event = ++slab.ev_pull;
+        A.nbr[0] = me > 0 ? me - 1 : -1;
+        A.nbr[1] = me + 1 < slab.world ? me + 1 : -1;
+        A.mine = flags(me);
+        for (int d = 0; d < 2; ++d) A.peer[d] = A.nbr[d] >= 0 ? flags(A.nbr[d]) : nullptr;
+        int nj = 0;
+        for (float* fp : fields) {
+            const int phys = phys_index(fp);
+            PullJob up{}, dn{};
+            if (A.nbr[0] >= 0) {  // my top halo rows = the last rows the upper neighbour owns
+                up.rows = slab.own0[me] - slab.row0[me];
+                up.dst = fp;
+                up.src = peer_field(me - 1, phys) + (size_t)(slab.row0[me] - slab.row0[me - 1]) * g.pitch;
+            }
+            if (A.nbr[1] >= 0) {  // my bottom halo rows = the first rows the lower neighbour owns
+                dn.rows = slab.row0[me] + slab.rows[me] - slab.own0[me + 1];
+                dn.dst = fp + (size_t)(slab.own0[me + 1] - slab.row0[me]) * g.pitch;
+                dn.src = peer_field(me + 1, phys) + (size_t)(slab.own0[me + 1] - slab.row0[me + 1]) * g.pitch;
+            }
+            A.job[nj++] = up;
+            A.job[nj++] = dn;
+        }
+        A.njobs = nj;
+        LAUNCH("k_slab_pull", stream, (k_slab_pull<<<dim3(24, nj), 256, 0, stream>>>(A)));
+        return 0;
+    }
+    int barrier() {
+        if (!is_slab()) return 0;
+        BarrierArgs A{};
+        A.event = ++slab.ev_bar; A.me = slab.rank; A.world = slab.world; A.mine = flags(slab.rank);
+        for (int r = 0; r < slab.world; ++r) A.peer[r] = flags(r);
+        LAUNCH("k_slab_barrier", stream, (k_slab_barrier<<<1, 32, 0, stream>>>(A)));
+        return 0;
+    }
+    // Where the owners keep field `fp` (f = slot 0/1 of the advect gather table).
+    void fill_table(SlabTable& t, int f, const float* fp) const {
+        t.world = slab.world;
+        for (int r = 0; r <= slab.world; ++r) t.own0[r] = slab.own0[r];
+        const int phys = phys_index(fp);
+        for (int r = 0; r < slab.world; ++r) { t.row0[r] = slab.row0[r]; t.base[f][r] = peer_field(r, phys); }
     }
 };
 
 struct fruid_fluid { FieldSet s; };    // buf: 0=u 1=v 2=u_prev 3=v_prev 4=scratch (lib.rs:247-253) 5=add_source temporary
 struct fruid_density { FieldSet s; };  // buf: 0=dens 1=dens_prev 2=scratch (lib.rs:210-214) 3=add_source temporary
+
+// ---- slab (multi-GPU) step schedules ---------------------------------------------------------
+// Same operator sequence as op_vel_step / op_dens_step; every operator runs on all local rows it
+// can (owned + halo), so a result stays valid a few rows beyond the owned ones and halo exchanges
+// are needed only where the validity margin m (rows beyond the owned rows) runs out:
+//   exchange -> m = 12;  T fused sweeps: m -> m - T;  divergence / gradient: m -> m - 1.
+// Advection gathers from the OWNER of each tap through peer memory, between two all-rank
+// barriers (everyone has finished writing / reading the gathered fields).
+static int project_slab(FieldSet& S, float*& u, float*& v, float*& p, float*& div, int T) {
+    const Geom& g = S.g;
+    cudaStream_t st = S.stream;
+    const std::function<int(float*)> xch = [&S](float* f) { return S.exchange({f}); };
+    const float sx = -0.5f / (float)g.nx, sy = -0.5f / (float)g.ny;
+    LAUNCH("k_divergence4", st, (k_divergence4<<<vec_grid(g), vec_block(), 0, st>>>(div, nullptr, u, v, g, sx, sy)));  // m: 12 -> 11
+    TRY(op_lin_solve(B_POSITIVE, p, div, S.buf[4], g, 1.0f, 4.0f, S.iters, T, st, true, false, 0.f, nullptr, &xch));     // m = 2
+    const float gx = -0.5f * (float)g.nx, gy = -0.5f * (float)g.ny;
+    LAUNCH("k_gradient4", st, (k_gradient4<<<vec_grid(g), vec_block(), 0, st>>>(u, v, p, g, gx, gy)));                  // m = 1
+    return 0;
+}
+
+static int op_vel_step_slab(FieldSet& S, float visc, float dt) {
+    TRY(S.need_peers());
+    const Geom& g = S.g;
+    cudaStream_t st = S.stream;
+    const int T = S.slab_fused();
+    float *&u = S.buf[0], *&v = S.buf[1], *&u0 = S.buf[2], *&v0 = S.buf[3], *&s = S.buf[4];
+    const std::function<int(float*)> xch = [&S](float* f) { return S.exchange({f}); };
+    const float a = ((dt * visc) * (float)g.nx) * (float)g.ny, c = 1.0f + 4.0f * a;
+    TRY(S.exchange({u, v, u0, v0}));                                                               // m = 12 everywhere
+    TRY(op_add_source(u, u0, v, v0, g, dt, st));                                                   // lib.rs:190-191
+    TRY(op_lin_solve(B_NEGX, u0, u, s, g, a, c, S.iters, T, st, false, false, 0.f, nullptr, &xch)); // lib.rs:194, m = 2
+    TRY(op_lin_solve(B_NEGY, v0, v, s, g, a, c, S.iters, T, st, false, false, 0.f, nullptr, &xch)); // lib.rs:197, m = 2
+    TRY(S.exchange({u0, v0}));                                                                     // m = 12
+    TRY(project_slab(S, u0, v0, u, v, T));                                                         // lib.rs:199
+    TRY(S.barrier());                          // every rank has finished writing u0, v0
+    {
+        SlabTable tab{};
+        S.fill_table(tab, 0, u0);
+        S.fill_table(tab, 1, v0);
+        float* d[2] = {u, v};
+        const float* d0[2] = {u0, v0};
+        const int b[2] = {B_NEGX, B_NEGY};
+        const int ly0 = std::max(S.own_lo(), 1 - g.gy0), ly1 = std::min(S.own_hi(), g.gh - 1 - g.gy0);
+        TRY(op_advect(2, d, d0, b, u0, v0, g, dt, st, &tab, ly0, ly1));                            // lib.rs:204-205
+    }
+    TRY(S.barrier());                          // every rank has finished reading u0, v0
+    TRY(S.exchange({u, v}));                                                                       // m = 12
+    return project_slab(S, u, v, u0, v0, T);                                                       // lib.rs:207
+}
+
+static int op_dens_step_slab(FieldSet& S, const float* u, const float* v, float diff, float dt) {
+    TRY(S.need_peers());
+    const Geom& g = S.g;
+    cudaStream_t st = S.stream;
+    const int T = S.slab_fused();
+    float *&x = S.buf[0], *&x0 = S.buf[1], *&s = S.buf[2];
+    const std::function<int(float*)> xch = [&S](float* f) { return S.exchange({f}); };
+    const float a = ((dt * diff) * (float)g.nx) * (float)g.ny, c = 1.0f + 4.0f * a;
+    TRY(S.exchange({x, x0}));
+    TRY(op_add_source(x, x0, nullptr, nullptr, g, dt, st));                                          // lib.rs:172
+    TRY(op_lin_solve(B_POSITIVE, x0, x, s, g, a, c, S.iters, T, st, false, false, 0.f, nullptr, &xch)); // lib.rs:175
+    TRY(S.barrier());
+    SlabTable tab{};
+    S.fill_table(tab, 0, x0);
+    float* d[1] = {x};
+    const float* d0[1] = {x0};
+    const int b[1] = {B_POSITIVE};
+    const int ly0 = std::max(S.own_lo(), 1 - g.gy0), ly1 = std::min(S.own_hi(), g.gh - 1 - g.gy0);
+    TRY(op_advect(1, d, d0, b, u, v, g, dt, st, &tab, ly0, ly1));                                   // lib.rs:178
+    return S.barrier();
+}
 
 #define NEED(h) do { if (!(h)) return fail(FRUID_ERR_BAD_ARG, "null handle"); CU(cudaSetDevice((h)->s.device)); } while (0)
 
@@ -357,6 +579,25 @@ extern "C" int fruid_fluid_create(size_t w, size_t h, fruid_fluid_t** out) {
     *out = f;
     return 0;
 }
+// Multi-GPU: rank `rank` of `world` owns a y-slab of the global w x gh field (one process per GPU).
+extern "C" int fruid_fluid_create_slab(size_t w, size_t gh, int rank, int world, fruid_fluid_t** out) {
+    if (!out) return fail(FRUID_ERR_BAD_ARG, "null out pointer");
+    *out = nullptr;
+    fruid_fluid* f = new (std::nothrow) fruid_fluid();
+    if (!f) return fail(FRUID_ERR_OOM, "host allocation failed");
+    int r = f->s.init(w, gh, 6, rank, world);
+    if (r) { f->s.release(); delete f; return r; }
+    *out = f;
+    return 0;
+}
+extern "C" int fruid_fluid_ipc_export(fruid_fluid_t* f, void* handle64) { NEED(f); return f->s.ipc_export(handle64); }
+extern "C" int fruid_fluid_ipc_attach(fruid_fluid_t* f, int peer, const void* handle64) { NEED(f); return f->s.ipc_attach(peer, handle64); }
+extern "C" int fruid_fluid_slab_rows(const fruid_fluid_t* f, size_t* y0, size_t* y1) {
+    if (!f || !y0 || !y1) return fail(FRUID_ERR_BAD_ARG, "null pointer");
+    *y0 = (size_t)f->s.slab.own0[f->s.slab.rank];
+    *y1 = (size_t)f->s.slab.own0[f->s.slab.rank + 1];
+    return 0;
+}
 extern "C" int fruid_fluid_destroy(fruid_fluid_t* f) {
     if (!f) return 0;
     cudaSetDevice(f->s.device);
@@ -365,7 +606,7 @@ extern "C" int fruid_fluid_destroy(fruid_fluid_t* f) {
     return 0;
 }
 extern "C" size_t fruid_fluid_width(const fruid_fluid_t* f) { return f ? (size_t)f->s.g.w : 0; }
-extern "C" size_t fruid_fluid_height(const fruid_fluid_t* f) { return f ? (size_t)f->s.g.h : 0; }
+extern "C" size_t fruid_fluid_height(const fruid_fluid_t* f) { return f ? (size_t)f->s.g.gh : 0; }
 extern "C" int fruid_fluid_upload(fruid_fluid_t* f, int field, const float* host) { NEED(f); return f->s.upload(field, host); }
 extern "C" int fruid_fluid_download(fruid_fluid_t* f, int field, float* host) {
     NEED(f);
@@ -377,6 +618,7 @@ extern "C" int fruid_fluid_set_fused_sweeps(fruid_fluid_t* f, int t) { NEED(f); 
 extern "C" int fruid_fluid_step(fruid_fluid_t* f, float dt, float visc) {
     NEED(f);
     FieldSet& s = f->s;
+    if (s.is_slab()) return op_vel_step_slab(s, visc, dt);
     return op_vel_step(s.buf[0], s.buf[1], s.buf[2], s.buf[3], s.buf[4], s.buf[5], s.g, visc, dt, s.iters, s.fused, s.stream);
 }
 extern "C" int fruid_fluid_step_n(fruid_fluid_t* f, float dt, float visc, int n) {
@@ -386,7 +628,7 @@ extern "C" int fruid_fluid_step_n(fruid_fluid_t* f, float dt, float visc, int n)
     return 0;
 }
 extern "C" void* fruid_fluid_stream(fruid_fluid_t* f) { return f ? (void*)f->s.stream : nullptr; }
-extern "C" int fruid_fluid_sync(fruid_fluid_t* f) { NEED(f); CU(cudaStreamSynchronize(f->s.stream)); CU(cudaGetLastError()); return 0; }
+extern "C" int fruid_fluid_sync(fruid_fluid_t* f) { NEED(f); CU(cudaStreamSynchronize(f->s.stream)); CU(cudaGetLastError()); return f->s.check_peer_error(); }
 
 extern "C" int fruid_density_create(size_t w, size_t h, fruid_density_t** out) {
     if (!out) return fail(FRUID_ERR_BAD_ARG, "null out pointer");
@@ -398,6 +640,18 @@ extern "C" int fruid_density_create(size_t w, size_t h, fruid_density_t** out) {
     *out = d;
     return 0;
 }
+extern "C" int fruid_density_create_slab(size_t w, size_t gh, int rank, int world, fruid_density_t** out) {
+    if (!out) return fail(FRUID_ERR_BAD_ARG, "null out pointer");
+    *out = nullptr;
+    fruid_density* d = new (std::nothrow) fruid_density();
+    if (!d) return fail(FRUID_ERR_OOM, "host allocation failed");
+    int r = d->s.init(w, gh, 4, rank, world);
+    if (r) { d->s.release(); delete d; return r; }
+    *out = d;
+    return 0;
+}
+extern "C" int fruid_density_ipc_export(fruid_density_t* d, void* handle64) { NEED(d); return d->s.ipc_export(handle64); }
+extern "C" int fruid_density_ipc_attach(fruid_density_t* d, int peer, const void* handle64) { NEED(d); return d->s.ipc_attach(peer, handle64); }
 extern "C" int fruid_density_destroy(fruid_density_t* d) {
     if (!d) return 0;
     cudaSetDevice(d->s.device);
@@ -429,13 +683,18 @@ extern "C" int fruid_density_step_dev(fruid_density_t* d, fruid_fluid_t* vel, fl
     if (!vel) return fail(FRUID_ERR_BAD_ARG, "null velocity handle");
     FieldSet& s = d->s;
     FieldSet& vs = vel->s;
-    if (vs.g.w != s.g.w || vs.g.h != s.g.h)
-        return fail(FRUID_ERR_SIZE_MISMATCH, "density %dx%d vs velocity %dx%d", s.g.w, s.g.h, vs.g.w, vs.g.h);
+    if (vs.g.w != s.g.w || vs.g.gh != s.g.gh)
+        return fail(FRUID_ERR_SIZE_MISMATCH, "density %dx%d vs velocity %dx%d", s.g.w, s.g.gh, vs.g.w, vs.g.gh);
     if (vs.device != s.device) return fail(FRUID_ERR_BAD_ARG, "density and velocity live on different devices");
     // u,v are produced on vel's stream and consumed on ours; order both ways.
     CU(cudaEventRecord(vs.ev, vs.stream));
     CU(cudaStreamWaitEvent(s.stream, vs.ev, 0));
-    TRY(op_dens_step(s.buf[0], s.buf[1], vs.buf[0], vs.buf[1], s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream));
+    if (s.is_slab() != vs.is_slab() || s.slab.world != vs.slab.world || s.slab.rank != vs.slab.rank)
+        return fail(FRUID_ERR_SIZE_MISMATCH, "density and velocity handles are decomposed differently");
+    if (s.is_slab())
+        TRY(op_dens_step_slab(s, vs.buf[0], vs.buf[1], diff, dt));
+    else
+        TRY(op_dens_step(s.buf[0], s.buf[1], vs.buf[0], vs.buf[1], s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream));
     CU(cudaEventRecord(s.ev, s.stream));
     CU(cudaStreamWaitEvent(vs.stream, s.ev, 0));
     return 0;
@@ -444,6 +703,7 @@ extern "C" int fruid_density_step_host(fruid_density_t* d, const float* u, const
     NEED(d);
     if (!u || !v) return fail(FRUID_ERR_BAD_ARG, "null velocity pointer");
     FieldSet& s = d->s;
+    if (s.is_slab()) return fail(FRUID_ERR_BAD_ARG, "slab-decomposed density needs a device-resident velocity (fruid_density_step_dev)");
     const size_t bytes = s.g.pitch * (size_t)s.g.h * sizeof(float);
     float *du = nullptr, *dv = nullptr;
     CU(cudaMallocAsync(&du, bytes, s.stream));
@@ -459,7 +719,7 @@ extern "C" int fruid_density_step_host(fruid_density_t* d, const float* u, const
     return 0;
 }
 extern "C" void* fruid_density_stream(fruid_density_t* d) { return d ? (void*)d->s.stream : nullptr; }
-extern "C" int fruid_density_sync(fruid_density_t* d) { NEED(d); CU(cudaStreamSynchronize(d->s.stream)); CU(cudaGetLastError()); return 0; }
+extern "C" int fruid_density_sync(fruid_density_t* d) { NEED(d); CU(cudaStreamSynchronize(d->s.stream)); CU(cudaGetLastError()); return d->s.check_peer_error(); }
 
 // Page-lock caller-owned host arrays (the Vec<f32> inside an Array2D has a fixed length for
 // the object's life) so uploads/downloads run at full PCIe rate.

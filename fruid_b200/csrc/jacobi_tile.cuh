@@ -180,13 +180,14 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
     const Geom& g = A.g;
     const int ox = kx * A.SX, oy = ky * A.SY;
     const int gx0 = ox + 4 * lane;  // global column of component .x
-    const int gyw = oy + wi * R;    // global row of this warp's row 0
+    const int gyw = oy + wi * R;    // LOCAL row of this warp's row 0
+    const int gyg = gyw + g.gy0;    // its GLOBAL row (boundary logic is global, addressing local)
     const bool negx = (A.b == B_NEGX), negy = (A.b == B_NEGY);
     const float a = A.a, c = A.c;
 
     EdgeFlags E;
     E.l1 = E.r0 = E.r1 = E.r2 = E.r3 = false;
-    E.negx = negx; E.negy = negy; E.h = g.h;
+    E.negx = negx; E.negy = negy; E.h = g.gh;
     if (EDGE) {
         E.l1 = (gx0 + 1 == 1);  // ox == 0 && lane == 0 (tile origins are multiples of 4)
         E.r0 = (gx0 + 0 == g.w - 2); E.r1 = (gx0 + 1 == g.w - 2); E.r2 = (gx0 + 2 == g.w - 2); E.r3 = (gx0 + 3 == g.w - 2);
@@ -219,7 +220,7 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
 #pragma unroll
             for (int r = 1; r <= R; ++r)
                 v[r - 1] = jac_row_full<MODE, EDGE>(v[r], v[r - 1], (r == R) ? hbot : v[r + 1], z[r - 1], a, c, E,
-                                                    sub, gyw + r - 1);
+                                                    sub, gyg + r - 1);
         }
         if (s + 1 > A.T) {  // odd T: move the rows back to v[1..R] for the store phase
 #pragma unroll
@@ -235,16 +236,20 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
 #pragma unroll
             for (int r = R - 1; r >= 0; --r)
                 v[r + 1] = jac_row_full<MODE, EDGE>(v[r], (r == 0) ? htop : v[r - 1], v[r + 1], z[r], a, c, E, EDGE,
-                                                    gyw + r);
+                                                    gyg + r);
         }
     }
     float4* const xr = v + 1;  // rows 0..R-1 of this warp
 
     // ---- store the cells that are H away from every non-domain tile edge -----------------
     (void)FULL;
-    const bool lastx = (kx == A.ntx - 1), lasty = (ky == A.nty - 1);
+    const bool lastx = (kx == A.ntx - 1);
     const int xlo = (kx == 0) ? 0 : ox + A.H, xhi = lastx ? g.w : ox + 128 - A.H;   // [xlo, xhi)
-    const int ylo = (ky == 0) ? 1 : oy + A.H, yhi = lasty ? g.h - 1 : oy + TH - A.H;  // interior rows only
+    // Rows (LOCAL indices): a local edge that is the domain edge needs no halo; one that is a slab
+    // cut is stale H rows deep.  Only interior rows are stored here; border rows follow below.
+    const bool top_dom = (g.gy0 == 0), bot_dom = (g.gy0 + g.h == g.gh);
+    const int ylo = (ky == 0 && top_dom) ? 1 : oy + A.H;
+    const int yhi = (ky == A.nty - 1) ? (bot_dom ? g.h - 1 : min(oy + TH - A.H, g.h - A.H)) : oy + TH - A.H;
     const bool v0 = gx0 + 0 >= xlo && gx0 + 0 < xhi, v1 = gx0 + 1 >= xlo && gx0 + 1 < xhi;
     const bool v2 = gx0 + 2 >= xlo && gx0 + 2 < xhi, v3 = gx0 + 3 >= xlo && gx0 + 3 < xhi;
     const bool vall = v0 && v1 && v2 && v3;
@@ -271,7 +276,7 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
         return;
     }
     if (A.fuse_src && A.z_out) {  // the updated right-hand side, all rows of my output band (border rows too)
-        const int zlo = (ky == 0) ? 0 : oy + A.H, zhi = lasty ? g.h : oy + TH - A.H;
+        const int zlo = (ky == 0 && top_dom) ? 0 : ylo, zhi = (yhi == g.h - 1 && bot_dom) ? g.h : yhi;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int gy = gyw + r;
@@ -308,7 +313,8 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
             if (v2) row[gx0 + 2] = f.z;
             if (v3) row[gx0 + 3] = f.w;
         }
-        if (gy == 1 || gy == g.h - 2) {
+        const int gyglob = gy + g.gy0;
+        if (gyglob == 1 || gyglob == g.gh - 2) {
             // border row(s) mirrored from this row (lib.rs:36-37) and their corners (lib.rs:40-43):
             // corner = 0.5*(row-edge + col-edge) = 0.5*(sy*v + sx*v), v = diagonal interior cell;
             // f already holds sx*v in the border columns.
@@ -320,9 +326,9 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
             if (gx0 + 3 == g.w - 1) e.w = fmul(0.5f, fadd(sgn(negy, f.z), f.w));
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
-                if (side == 0 && gy != 1) continue;
-                if (side == 1 && gy != g.h - 2) continue;
-                float* brow = A.out + (size_t)(side == 0 ? 0 : g.h - 1) * g.pitch;
+                if (side == 0 && gyglob != 1) continue;
+                if (side == 1 && gyglob != g.gh - 2) continue;
+                float* brow = A.out + (size_t)(side == 0 ? gy - 1 : gy + 1) * g.pitch;
                 if (v0) brow[gx0 + 0] = e.x;
                 if (v1) brow[gx0 + 1] = e.y;
                 if (v2) brow[gx0 + 2] = e.z;
@@ -403,7 +409,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_jacobi_tile(const __grid_constan
             }
         }
         const int ox = kx * A.SX, oy = ky * A.SY;
-        const bool edge = (kx == 0) || (ky == 0) || (ox + 128 >= A.g.w - 1) || (oy + TH >= A.g.h - 1);
+        const bool edge = (kx == 0) || (ox + 128 >= A.g.w - 1) || (oy + A.g.gy0 <= 1) || (oy + TH + A.g.gy0 >= A.g.gh - 1) ||
+                          (ky == 0) || (ky == A.nty - 1);  // slab cuts take the general store path too
         if (edge)
             jacobi_tile_body<R, NW, MODE, true>(A, kx, ky, v, z, halo);
         else

@@ -18,7 +18,9 @@ __device__ __forceinline__ float4 neg4(bool neg, float4 v) { return neg ? make_f
 //   x[0,j] = sx*x[1,j], x[nx+1,j] = sx*x[nx,j]            lib.rs:31-32
 //   x[i,0] = sy*x[i,1], x[i,ny+1] = sy*x[i,ny]            lib.rs:36-37
 //   corner = 0.5*(row-edge + col-edge)                    lib.rs:40-43
-__device__ __forceinline__ void store_row4_bnd(float* __restrict__ out, const Geom& g, int b, int gx0, int gy, float4 val) {
+// `ly` is the LOCAL row (its global row is ly + g.gy0); rows ly-1 / ly+1 must exist locally.
+__device__ __forceinline__ void store_row4_bnd(float* __restrict__ out, const Geom& g, int b, int gx0, int ly, float4 val) {
+    const int gy = ly + g.gy0;
     const bool negx = (b == B_NEGX), negy = (b == B_NEGY);
     const int kr = g.w - 1 - gx0;  // component index of the right border column (0..3 if inside this float4)
     if (gx0 == 0) val.x = sgn(negx, val.y);
@@ -28,7 +30,7 @@ __device__ __forceinline__ void store_row4_bnd(float* __restrict__ out, const Ge
     const float extra = sgn(negx, val.w);  // border value at gx0+4 when kr == 4 (I own column w-2 in .w)
     // kr == 0: my .x is the right border but its source is the previous thread's .w -> it writes it.
     const bool w0 = (kr != 0) && (gx0 + 0 < g.w), w1 = gx0 + 1 < g.w, w2 = gx0 + 2 < g.w, w3 = gx0 + 3 < g.w;
-    float* row = out + (size_t)gy * g.pitch + gx0;
+    float* row = out + (size_t)ly * g.pitch + gx0;
     if (w0 && w3) {
         *reinterpret_cast<float4*>(row) = val;
     } else {
@@ -49,7 +51,7 @@ __device__ __forceinline__ void store_row4_bnd(float* __restrict__ out, const Ge
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
             if (side == 0 ? !top : !bot) continue;
-            float* brow = out + (size_t)(side == 0 ? 0 : g.ny + 1) * g.pitch + gx0;
+            float* brow = out + (size_t)(side == 0 ? ly - 1 : ly + 1) * g.pitch + gx0;
             if (w0 && w3) {
                 *reinterpret_cast<float4*>(brow) = e;
             } else {
@@ -90,8 +92,8 @@ __device__ __forceinline__ void edge_vals(const float* __restrict__ f, const Geo
 __global__ void k_divergence4(float* __restrict__ div, float* __restrict__ p, const float* __restrict__ u,
                               const float* __restrict__ v, Geom g, float sx, float sy) {
     const int gx0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
-    const int gy = blockIdx.y * blockDim.y + threadIdx.y + 1;
-    if (gx0 >= g.w || gy > g.ny) return;
+    const int gy = blockIdx.y * blockDim.y + threadIdx.y + 1;  // LOCAL row; needs rows gy-1, gy+1
+    if (gx0 >= g.w || gy > g.h - 2) return;
     const size_t k = (size_t)gy * g.pitch + gx0;
     const float4 uc = ld4(u + k), vu = ld4(v + k - g.pitch), vd = ld4(v + k + g.pitch);
     float ul, ur;
@@ -110,8 +112,8 @@ __global__ void k_divergence4(float* __restrict__ div, float* __restrict__ p, co
 __global__ void k_gradient4(float* __restrict__ u, float* __restrict__ v, const float* __restrict__ p, Geom g, float gxs,
                             float gys) {
     const int gx0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
-    const int gy = blockIdx.y * blockDim.y + threadIdx.y + 1;
-    if (gx0 >= g.w || gy > g.ny) return;
+    const int gy = blockIdx.y * blockDim.y + threadIdx.y + 1;  // LOCAL row; needs rows gy-1, gy+1
+    if (gx0 >= g.w || gy > g.h - 2) return;
     const size_t k = (size_t)gy * g.pitch + gx0;
     const float4 pc = ld4(p + k), pu = ld4(p + k - g.pitch), pd = ld4(p + k + g.pitch);
     float pl, pr;
@@ -130,14 +132,46 @@ __global__ void k_gradient4(float* __restrict__ u, float* __restrict__ v, const 
     store_row4_bnd(v, g, B_NEGY, gx0, gy, vn);
 }
 
+// Where the rows of a field live when it is y-slab decomposed over several GPUs: rank r holds
+// global rows [row0[r], row0[r] + rows[r]) ... owned rows [own0[r], own0[r+1]) at base[f][r]
+// (a peer-mapped pointer, NVLink).  A gather tap at global row gj reads the copy of its OWNER.
+struct SlabTable {
+    int world;                 // 1 = single GPU (base[.][0] = local field, row0[0] = 0)
+    int own0[9];               // owned global rows of rank r: [own0[r], own0[r+1])
+    int row0[8];               // global row of local row 0 of rank r
+    const float* base[2][8];   // [field][rank]
+};
+__device__ __forceinline__ const float* slab_row(const SlabTable& t, int f, int gj, size_t pitch) {
+    int r = 0;
+#pragma unroll 1
+    while (r + 1 < t.world && gj >= t.own0[r + 1]) ++r;
+    return t.base[f][r] + (size_t)(gj - t.row0[r]) * pitch;
+}
+template <bool MULTI>
+__device__ __forceinline__ float gather_slab(const SlabTable& tab, int f, const float* __restrict__ d0, const Geom& g,
+                                             const Trace& t) {
+    float a00, a01, a10, a11;
+    if (MULTI) {
+        const float* r0 = slab_row(tab, f, t.j0, g.pitch) + t.i0;
+        const float* r1 = slab_row(tab, f, t.j0 + 1, g.pitch) + t.i0;
+        a00 = __ldg(r0); a10 = __ldg(r0 + 1); a01 = __ldg(r1); a11 = __ldg(r1 + 1);
+    } else {
+        const float* r0 = d0 + (size_t)t.j0 * g.pitch + t.i0;
+        a00 = __ldg(r0); a10 = __ldg(r0 + 1); a01 = __ldg(r0 + g.pitch); a11 = __ldg(r0 + g.pitch + 1);
+    }
+    return mixf(mixf(a00, a01, t.t1), mixf(a10, a11, t.t1), t.s1);
+}
+
 // advect (src/lib.rs:84-126) for NF fields sharing one back-trace, four cells per thread.
-template <int NF>
+// Output rows: local rows [ly0, ly1) (all interior rows on one GPU; the owned rows of a slab).
+template <int NF, bool MULTI>
 __global__ void k_advect4(AdvectArgs a, const float* __restrict__ u, const float* __restrict__ v, Geom g, float dt0,
-                          float dt1, float xmax, float ymax) {
+                          float dt1, float xmax, float ymax, int ly0, int ly1, const __grid_constant__ SlabTable tab) {
     const int gx0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
-    const int gy = blockIdx.y * blockDim.y + threadIdx.y + 1;
-    if (gx0 >= g.w || gy > g.ny) return;
-    const size_t k = (size_t)gy * g.pitch + gx0;
+    const int ly = blockIdx.y * blockDim.y + threadIdx.y + ly0;
+    if (gx0 >= g.w || ly >= ly1) return;
+    const int gy = ly + g.gy0;  // global row: the back-trace and the gather use global coordinates
+    const size_t k = (size_t)ly * g.pitch + gx0;
     const float4 uc = ld4(u + k), vc = ld4(v + k);
     Trace t[4];
     t[0] = backtrace(gx0 + 0, gy, uc.x, vc.x, dt0, dt1, xmax, ymax);
@@ -147,11 +181,11 @@ __global__ void k_advect4(AdvectArgs a, const float* __restrict__ u, const float
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
         float4 r;
-        r.x = gather(a.d0[f], g, t[0]);
-        r.y = gather(a.d0[f], g, t[1]);
-        r.z = gather(a.d0[f], g, t[2]);
-        r.w = gather(a.d0[f], g, t[3]);
-        store_row4_bnd(a.d[f], g, a.b[f], gx0, gy, r);
+        r.x = gather_slab<MULTI>(tab, f, a.d0[f], g, t[0]);
+        r.y = gather_slab<MULTI>(tab, f, a.d0[f], g, t[1]);
+        r.z = gather_slab<MULTI>(tab, f, a.d0[f], g, t[2]);
+        r.w = gather_slab<MULTI>(tab, f, a.d0[f], g, t[3]);
+        store_row4_bnd(a.d[f], g, a.b[f], gx0, ly, r);
     }
 }
 

@@ -1,0 +1,128 @@
+// slab_comm.cuh -- multi-GPU y-slab decomposition over NVLink peer memory.
+//
+// One process per GPU.  Rank r owns global rows [own0[r], own0[r+1]) and keeps HALO extra rows
+// of each neighbour on either side.  All device state of a handle lives in ONE allocation
+// (flags + fields) that is exported with cudaIpcGetMemHandle and mapped by every peer, so
+//   * halo rows are PULLED from the neighbour's owned rows with plain peer loads, and
+//   * advection gathers at any distance read the owner's copy directly (slab_row()).
+// Cross-GPU ordering uses monotonically increasing epoch flags in peer memory, written with
+// system-scope release and polled with system-scope acquire.  Every rank executes the same
+// sequence of events, a wait only ever targets an event its peer signals without waiting for
+// anything later, hence no cycles.  Spin loops give up after SPIN_TIMEOUT_NS and raise an error
+// word instead of hanging the GPU.
+#pragma once
+#include "common.cuh"
+
+namespace fruid {
+
+constexpr int SLAB_HALO = 12;       // rows kept of each neighbour: >= fused sweeps (10) + 2
+constexpr int SLAB_MAX_T = 10;      // fused sweeps per launch allowed in slab mode
+constexpr int SLAB_MAX_RANKS = 8;
+constexpr size_t SLAB_FLAG_BYTES = 4096;
+constexpr unsigned long long SPIN_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
+
+// Flag block at the start of every rank's allocation (written by peers, read locally).
+struct SlabFlags {
+    int ready[SLAB_MAX_RANKS];     // ready[s]    >= e : rank s has produced everything up to event e
+    int consumed[SLAB_MAX_RANKS];  // consumed[s] >= e : rank s has finished reading my rows for event e
+    int bar[SLAB_MAX_RANKS];       // bar[s]      >= e : rank s has reached barrier e
+    int error;                     // set when a spin timed out
+    int pull_done;                 // CTA counter of the running pull kernel (self-resetting)
+};
+
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Spin until *flag >= e (false on timeout).
+__device__ __forceinline__ bool spin_until(const int* flag, int e, int* err) {
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(flag) < e) {
+        if (globaltimer_ns() - t0 > SPIN_TIMEOUT_NS) {
+            *err = 1;
+            return false;
+        }
+        __nanosleep(64);
+    }
+    return true;
+}
+
+struct PullJob {           // copy `rows` rows of `pitch` floats from a peer's field into my halo rows
+    const float* src;      // peer-mapped pointer to the first row to copy
+    float* dst;
+    int rows;
+};
+struct PullArgs {
+    PullJob job[8];        // up to 4 fields x 2 directions
+    int njobs;
+    size_t pitch;
+    int event;             // epoch of this exchange
+    int me;
+    int nbr[2];            // neighbour ranks (-1 = none): up, down
+    SlabFlags* mine;       // my flag block
+    SlabFlags* peer[2];    // neighbours' flag blocks (peer-mapped)
+};
+
+// One halo exchange event.  grid.x = CTAs per job, grid.y = njobs.
+//  1. announce that my rows are ready (stream order put my producing kernels before this launch),
+//  2. wait for the neighbours' announcements, pull their rows into my halo rows,
+//  3. the last CTA tells the neighbours that I am done reading and waits until they are done
+//     reading mine, so that whatever follows on this stream may overwrite the exchanged fields.
+__global__ void k_slab_pull(const __grid_constant__ PullArgs A) {
+    __shared__ int s_ok;
+    SlabFlags* mine = A.mine;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        __threadfence_system();
+        for (int d = 0; d < 2; ++d)
+            if (A.nbr[d] >= 0) st_release_sys(&A.peer[d]->ready[A.me], A.event);
+    }
+    const PullJob j = A.job[blockIdx.y];
+    const int d = blockIdx.y & 1;  // jobs alternate up / down
+    if (threadIdx.x == 0) s_ok = (A.nbr[d] < 0) ? 0 : (spin_until(&mine->ready[A.nbr[d]], A.event, &mine->error) ? 1 : 0);
+    __syncthreads();
+    if (s_ok && j.rows > 0) {
+        const size_t n4 = (size_t)j.rows * A.pitch / 4;
+        const float4* src = reinterpret_cast<const float4*>(j.src);
+        float4* dst = reinterpret_cast<float4*>(j.dst);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+            dst[i] = __ldcv(src + i);  // peer memory: bypass L1
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const int total = gridDim.x * gridDim.y;
+        if (atomicAdd(&mine->pull_done, 1) == total - 1) {
+            mine->pull_done = 0;
+            for (int dd = 0; dd < 2; ++dd)
+                if (A.nbr[dd] >= 0) st_release_sys(&A.peer[dd]->consumed[A.me], A.event);
+            for (int dd = 0; dd < 2; ++dd)
+                if (A.nbr[dd] >= 0) spin_until(&mine->consumed[A.nbr[dd]], A.event, &mine->error);
+        }
+    }
+}
+
+struct BarrierArgs {
+    int event, me, world;
+    SlabFlags* mine;
+    SlabFlags* peer[SLAB_MAX_RANKS];
+};
+// All-ranks barrier (before / after the peer gathers of advect).
+__global__ void k_slab_barrier(const __grid_constant__ BarrierArgs A) {
+    const int t = threadIdx.x;
+    if (t < A.world && t != A.me) {
+        __threadfence_system();
+        st_release_sys(&A.peer[t]->bar[A.me], A.event);
+        spin_until(&A.mine->bar[t], A.event, &A.mine->error);
+    }
+}
+
+}  // namespace fruid

@@ -123,6 +123,23 @@ int fruid_density_step_host(fruid_density_t *d, const float *u, const float *v, 
 int fruid_density_sync(fruid_density_t *d);
 void *fruid_density_stream(fruid_density_t *d);
 
+/* ---- Multi-GPU y-slabs: one process per GPU -----------------------------------
+ * Rank `rank` of `world` (<= 8) owns global rows [y0, y1) of the w x gh field plus 12 halo rows
+ * of each neighbour.  After creation every rank exports a 64-byte CUDA IPC handle of its device
+ * allocation, the ranks exchange them out of band (the Python host side uses torch.distributed),
+ * and each rank attaches all peers.  step()/step_dev() then run the same operator sequence as
+ * on one GPU with halo rows pulled over NVLink and advection gathers served from the owner's
+ * memory; results are bit-identical to the single-GPU run.  upload/download move the OWNED rows
+ * (dense w floats per row); inject takes global coordinates.  Every rank must issue the same
+ * sequence of step calls. */
+int fruid_fluid_create_slab(size_t w, size_t gh, int rank, int world, fruid_fluid_t **out);
+int fruid_fluid_ipc_export(fruid_fluid_t *f, void *handle64);
+int fruid_fluid_ipc_attach(fruid_fluid_t *f, int peer_rank, const void *handle64);
+int fruid_fluid_slab_rows(const fruid_fluid_t *f, size_t *y0, size_t *y1);
+int fruid_density_create_slab(size_t w, size_t gh, int rank, int world, fruid_density_t **out);
+int fruid_density_ipc_export(fruid_density_t *d, void *handle64);
+int fruid_density_ipc_attach(fruid_density_t *d, int peer_rank, const void *handle64);
+
 /* ---- Per-operator entry points (parity tests / profiling) ---------------
  * Host arrays in, host arrays out; each call uploads, runs the same kernels the
  * step uses, and downloads.  `fused` = Jacobi sweeps per launch (0 = default).
