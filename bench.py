@@ -361,7 +361,7 @@ def run_e2e(args, fb, torch, sc, w, h):
 
 def run_b200_multi(args, fb, dist, rank, world, local):
     """N GPUs of one node, one process per GPU: the scene is y-slab decomposed (rank r owns rows
-    [r*h/N, (r+1)*h/N) plus 12 halo rows of each neighbour); halo rows and advection gathers move
+    [r*h/N, (r+1)*h/N) plus 22 halo rows of each neighbour); halo rows and advection gathers move
     over NVLink peer memory inside the library's kernels.  WEAK scaling: w x (w*N) cells, i.e. the
     single-GPU workload per GPU.  Time = max over ranks of the CUDA-event time of the K steps,
     bracketed by barriers."""
@@ -406,6 +406,15 @@ def run_b200_multi(args, fb, dist, rank, world, local):
     ms = float(ms.item())
     value = w * h * args.steps / (ms * 1e-3)
 
+    # per-kernel timing pass (rank 0's view; includes the time spent waiting for peers)
+    _lib.profile_enable(True)
+    for _ in range(3):
+        scene_step()
+    stats = _lib.profile_report()
+    _lib.profile_enable(False)
+    dist.barrier()
+    kernels_ms = {k: [n // 3, round(t / 3, 4)] for k, (n, t) in sorted(stats.items())}
+
     # end to end: every step each rank uploads its rows of the three source fields and downloads
     # its rows of the density (host <-> device inside the timed region), wall clock, max over ranks
     rows = sim.y1 - sim.y0
@@ -440,7 +449,7 @@ def run_b200_multi(args, fb, dist, rank, world, local):
         cfg["workload"] = (f"{w}x{h} scene step y-slab decomposed over {world} GPUs ({w}x{h // world} cells per GPU, weak "
                            f"scaling of the {w}x{w} single-GPU workload); FluidSim::step + 1x DensitySim::step, K={ITERS}")
         cfg["grid"] = [w, h]
-        cfg["halo_rows"] = 12
+        cfg["halo_rows"] = 22
         line = {"metric": "cell-steps/sec", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak" if not args.rows else "custom", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -449,7 +458,7 @@ def run_b200_multi(args, fb, dist, rank, world, local):
                              "peak": 6551.4, "unit": "GB/s", "frac": bytes_per_cell_step() * value / world / 1e9 / 6551.4,
                              "traffic": None, "note": "per-GPU algorithmic bytes (188+60K per cell-step) / time; see the "
                                                       "N=1 line for the dominant kernel"},
-                "cpu_baseline": None, "impl": "b200"}
+                "cpu_baseline": None, "impl": "b200", "kernels_launches_ms_per_step_rank0": kernels_ms}
         print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -159,10 +159,17 @@ static inline int resolve_fused(const Geom& g, int iters, int fused) {
     if (fused <= 0) fused = jacobi_tile_default_fused(g, iters);
     return fused > iters ? iters : fused;
 }
+// Slab mode: validity margins (rows beyond the owned rows that hold correct values) of the
+// iterate and of the right-hand side, the margin the caller needs on return, and the halo
+// exchange to call when a block would run out of margin.  T fused sweeps cost the iterate T
+// rows of margin; the result also needs the right-hand side T-1 rows further out.
+struct SlabSolve {
+    int m_x, m_x0, need_final;
+    std::function<int(std::initializer_list<float*>)> exchange;
+};
 static int op_lin_solve(int b, float*& x, const float* x0, float*& scratch, const Geom& g, float a, float c,
                         int iters, int fused, cudaStream_t st, bool x_is_zero = false, bool fuse_src = false,
-                        float src_dt = 0.f, float* z_tmp = nullptr,
-                        const std::function<int(float*)>* between_blocks = nullptr) {
+                        float src_dt = 0.f, float* z_tmp = nullptr, SlabSolve* slab = nullptr) {
     if (iters < 2 || (iters & 1)) return fail(FRUID_ERR_ODD_ITERATIONS, "iterations must be even and >= 2, got %d", iters);
     if (degenerate(g)) {
         LAUNCH("k_serial_lin_solve", st, k_serial_lin_solve<<<1, 1, 0, st>>>(x, x0, scratch, g, a, c, b, iters));
@@ -180,17 +187,28 @@ static int op_lin_solve(int b, float*& x, const float* x0, float*& scratch, cons
     int done = 0;
     for (int k = 0; k < nblocks; ++k) {
         const int T = (iters - done + (nblocks - k) - 1) / (nblocks - k);  // spread evenly
-        prof_pre(st);
         const bool fs = fuse_src && k == 0;  // first block also performs add_source(x0, x, dt) -> z_tmp
-        if (jacobi_tile_launch(scratch, x, (fuse_src && k > 0) ? z_tmp : x0, g, a, c, b, T, (x_is_zero && k == 0) ? 1 : 0, st,
-                               fs ? 1 : 0, src_dt, (fs && nblocks > 1) ? z_tmp : nullptr) != 0)
+        const bool xz = x_is_zero && k == 0;
+        const float* rhs = (fuse_src && k > 0) ? z_tmp : x0;
+        if (slab) {  // refresh halo rows from the neighbours only when this block would run out of margin
+            const int req = (k + 1 == nblocks) ? slab->need_final : 0;
+            const bool xs = !xz && slab->m_x - T < req, zs = slab->m_x0 - (T - 1) < req;
+            if (xs && zs) { TRY(slab->exchange({x, const_cast<float*>(rhs)})); slab->m_x = slab->m_x0 = SLAB_HALO; }
+            else if (xs) { TRY(slab->exchange({x})); slab->m_x = SLAB_HALO; }
+            else if (zs) { TRY(slab->exchange({const_cast<float*>(rhs)})); slab->m_x0 = SLAB_HALO; }
+        }
+        prof_pre(st);
+        if (jacobi_tile_launch(scratch, x, rhs, g, a, c, b, T, xz ? 1 : 0, st, fs ? 1 : 0, src_dt,
+                               (fs && nblocks > 1) ? z_tmp : nullptr) != 0)
             return fail(FRUID_ERR_BAD_ARG, "fused sweeps T=%d not supported by the current tile config", T);
         TRY(launched("k_jacobi_tile", st));
         done += T;
         float* t = x; x = scratch; scratch = t;
-        // slab mode: the new iterate is valid SLAB_HALO - T rows beyond the owned rows; refresh
-        // the halo rows from the neighbours before the next block consumes them
-        if (between_blocks && k + 1 < nblocks) TRY((*between_blocks)(x));
+        if (slab) {  // rows beyond the owned ones that the block just produced correctly
+            const int stored = SLAB_HALO - (T + (T & 1));  // the tile kernel stores no closer than H to a slab cut
+            slab->m_x = std::min(std::min((xz ? SLAB_HALO : slab->m_x) - T, slab->m_x0 - (T - 1)), stored);
+            if (fs) slab->m_x0 = std::min(slab->m_x0, stored);  // z_tmp is written on the stored rows only
+        }
     }
     return 0;
 }
@@ -473,7 +491,7 @@ struct FieldSet {
             A.job[nj++] = dn;
         }
         A.njobs = nj;
-        LAUNCH("k_slab_pull", stream, (k_slab_pull<<<dim3(24, nj), 256, 0, stream>>>(A)));
+        LAUNCH("k_slab_pull", stream, (k_slab_pull<<<dim3(16, nj), 256, 0, stream>>>(A)));
         return 0;
     }
     int barrier() {
@@ -487,6 +505,8 @@ struct FieldSet {
     // Where the owners keep field `fp` (f = slot 0/1 of the advect gather table).
     void fill_table(SlabTable& t, int f, const float* fp) const {
         t.world = slab.world;
+        t.me = slab.rank;
+        t.my_lo = slab.own0[slab.rank]; t.my_hi = slab.own0[slab.rank + 1]; t.my_row0 = slab.row0[slab.rank];
         for (int r = 0; r <= slab.world; ++r) t.own0[r] = slab.own0[r];
         const int phys = phys_index(fp);
         for (int r = 0; r < slab.world; ++r) { t.row0[r] = slab.row0[r]; t.base[f][r] = peer_field(r, phys); }
@@ -506,12 +526,12 @@ struct fruid_density { FieldSet s; };  // buf: 0=dens 1=dens_prev 2=scratch (lib
 static int project_slab(FieldSet& S, float*& u, float*& v, float*& p, float*& div, int T) {
     const Geom& g = S.g;
     cudaStream_t st = S.stream;
-    const std::function<int(float*)> xch = [&S](float* f) { return S.exchange({f}); };
     const float sx = -0.5f / (float)g.nx, sy = -0.5f / (float)g.ny;
-    LAUNCH("k_divergence4", st, (k_divergence4<<<vec_grid(g), vec_block(), 0, st>>>(div, nullptr, u, v, g, sx, sy)));  // m: 12 -> 11
-    TRY(op_lin_solve(B_POSITIVE, p, div, S.buf[4], g, 1.0f, 4.0f, S.iters, T, st, true, false, 0.f, nullptr, &xch));     // m = 2
+    LAUNCH("k_divergence4", st, (k_divergence4<<<vec_grid(g), vec_block(), 0, st>>>(div, nullptr, u, v, g, sx, sy)));  // m: HALO -> HALO-1
+    SlabSolve ss{SLAB_HALO, SLAB_HALO - 1, 1, [&S](std::initializer_list<float*> f) { return S.exchange(f); }};
+    TRY(op_lin_solve(B_POSITIVE, p, div, S.buf[4], g, 1.0f, 4.0f, S.iters, T, st, true, false, 0.f, nullptr, &ss));
     const float gx = -0.5f * (float)g.nx, gy = -0.5f * (float)g.ny;
-    LAUNCH("k_gradient4", st, (k_gradient4<<<vec_grid(g), vec_block(), 0, st>>>(u, v, p, g, gx, gy)));                  // m = 1
+    LAUNCH("k_gradient4", st, (k_gradient4<<<vec_grid(g), vec_block(), 0, st>>>(u, v, p, g, gx, gy)));  // needs p one row out
     return 0;
 }
 
@@ -521,14 +541,18 @@ static int op_vel_step_slab(FieldSet& S, float visc, float dt) {
     cudaStream_t st = S.stream;
     const int T = S.slab_fused();
     float *&u = S.buf[0], *&v = S.buf[1], *&u0 = S.buf[2], *&v0 = S.buf[3], *&s = S.buf[4];
-    const std::function<int(float*)> xch = [&S](float* f) { return S.exchange({f}); };
+    float* const s2 = S.buf[5];
+    const auto xch = [&S](std::initializer_list<float*> f) { return S.exchange(f); };
     const float a = ((dt * visc) * (float)g.nx) * (float)g.ny, c = 1.0f + 4.0f * a;
-    TRY(S.exchange({u, v, u0, v0}));                                                               // m = 12 everywhere
-    TRY(op_add_source(u, u0, v, v0, g, dt, st));                                                   // lib.rs:190-191
-    TRY(op_lin_solve(B_NEGX, u0, u, s, g, a, c, S.iters, T, st, false, false, 0.f, nullptr, &xch)); // lib.rs:194, m = 2
-    TRY(op_lin_solve(B_NEGY, v0, v, s, g, a, c, S.iters, T, st, false, false, 0.f, nullptr, &xch)); // lib.rs:197, m = 2
-    TRY(S.exchange({u0, v0}));                                                                     // m = 12
-    TRY(project_slab(S, u0, v0, u, v, T));                                                         // lib.rs:199
+    TRY(S.exchange({u, v, u0, v0}));                                                   // margins = HALO everywhere
+    {   // add_source folded into the first block of each diffuse (lib.rs:190-197)
+        SlabSolve su{SLAB_HALO, SLAB_HALO, 0, xch};
+        TRY(op_lin_solve(B_NEGX, u0, u, s, g, a, c, S.iters, T, st, false, true, dt, s2, &su));
+        SlabSolve sv{SLAB_HALO, SLAB_HALO, 0, xch};
+        TRY(op_lin_solve(B_NEGY, v0, v, s, g, a, c, S.iters, T, st, false, true, dt, s2, &sv));
+    }
+    TRY(S.exchange({u0, v0}));
+    TRY(project_slab(S, u0, v0, u, v, T));                                             // lib.rs:199
     TRY(S.barrier());                          // every rank has finished writing u0, v0
     {
         SlabTable tab{};
@@ -538,11 +562,11 @@ static int op_vel_step_slab(FieldSet& S, float visc, float dt) {
         const float* d0[2] = {u0, v0};
         const int b[2] = {B_NEGX, B_NEGY};
         const int ly0 = std::max(S.own_lo(), 1 - g.gy0), ly1 = std::min(S.own_hi(), g.gh - 1 - g.gy0);
-        TRY(op_advect(2, d, d0, b, u0, v0, g, dt, st, &tab, ly0, ly1));                            // lib.rs:204-205
+        TRY(op_advect(2, d, d0, b, u0, v0, g, dt, st, &tab, ly0, ly1));                // lib.rs:204-205
     }
     TRY(S.barrier());                          // every rank has finished reading u0, v0
-    TRY(S.exchange({u, v}));                                                                       // m = 12
-    return project_slab(S, u, v, u0, v0, T);                                                       // lib.rs:207
+    TRY(S.exchange({u, v}));
+    return project_slab(S, u, v, u0, v0, T);                                           // lib.rs:207
 }
 
 static int op_dens_step_slab(FieldSet& S, const float* u, const float* v, float diff, float dt) {
@@ -551,11 +575,11 @@ static int op_dens_step_slab(FieldSet& S, const float* u, const float* v, float 
     cudaStream_t st = S.stream;
     const int T = S.slab_fused();
     float *&x = S.buf[0], *&x0 = S.buf[1], *&s = S.buf[2];
-    const std::function<int(float*)> xch = [&S](float* f) { return S.exchange({f}); };
+    float* const s2 = S.buf[3];
     const float a = ((dt * diff) * (float)g.nx) * (float)g.ny, c = 1.0f + 4.0f * a;
     TRY(S.exchange({x, x0}));
-    TRY(op_add_source(x, x0, nullptr, nullptr, g, dt, st));                                          // lib.rs:172
-    TRY(op_lin_solve(B_POSITIVE, x0, x, s, g, a, c, S.iters, T, st, false, false, 0.f, nullptr, &xch)); // lib.rs:175
+    SlabSolve sd{SLAB_HALO, SLAB_HALO, 0, [&S](std::initializer_list<float*> f) { return S.exchange(f); }};
+    TRY(op_lin_solve(B_POSITIVE, x0, x, s, g, a, c, S.iters, T, st, false, true, dt, s2, &sd));  // lib.rs:172,175
     TRY(S.barrier());
     SlabTable tab{};
     S.fill_table(tab, 0, x0);
@@ -563,7 +587,7 @@ static int op_dens_step_slab(FieldSet& S, const float* u, const float* v, float 
     const float* d0[1] = {x0};
     const int b[1] = {B_POSITIVE};
     const int ly0 = std::max(S.own_lo(), 1 - g.gy0), ly1 = std::min(S.own_hi(), g.gh - 1 - g.gy0);
-    TRY(op_advect(1, d, d0, b, u, v, g, dt, st, &tab, ly0, ly1));                                   // lib.rs:178
+    TRY(op_advect(1, d, d0, b, u, v, g, dt, st, &tab, ly0, ly1));                       // lib.rs:178
     return S.barrier();
 }
 

@@ -137,23 +137,29 @@ __global__ void k_gradient4(float* __restrict__ u, float* __restrict__ v, const 
 // (a peer-mapped pointer, NVLink).  A gather tap at global row gj reads the copy of its OWNER.
 struct SlabTable {
     int world;                 // 1 = single GPU (base[.][0] = local field, row0[0] = 0)
+    int me;                    // my rank
+    int my_lo, my_hi, my_row0; // my owned global rows [my_lo, my_hi) and the global row of my local row 0:
+                               // taps inside them use the local field pointer (no table lookup)
     int own0[9];               // owned global rows of rank r: [own0[r], own0[r+1])
     int row0[8];               // global row of local row 0 of rank r
     const float* base[2][8];   // [field][rank]
 };
-__device__ __forceinline__ const float* slab_row(const SlabTable& t, int f, int gj, size_t pitch) {
+__device__ __noinline__ const float* slab_row_remote(const SlabTable& t, int f, int gj, size_t pitch) {
     int r = 0;
-#pragma unroll 1
     while (r + 1 < t.world && gj >= t.own0[r + 1]) ++r;
     return t.base[f][r] + (size_t)(gj - t.row0[r]) * pitch;
+}
+__device__ __forceinline__ const float* slab_row(const SlabTable& t, int f, const float* local, int gj, size_t pitch) {
+    if (gj >= t.my_lo && gj < t.my_hi) return local + (size_t)(gj - t.my_row0) * pitch;
+    return slab_row_remote(t, f, gj, pitch);  // rare: the tap belongs to another rank (peer memory)
 }
 template <bool MULTI>
 __device__ __forceinline__ float gather_slab(const SlabTable& tab, int f, const float* __restrict__ d0, const Geom& g,
                                              const Trace& t) {
     float a00, a01, a10, a11;
     if (MULTI) {
-        const float* r0 = slab_row(tab, f, t.j0, g.pitch) + t.i0;
-        const float* r1 = slab_row(tab, f, t.j0 + 1, g.pitch) + t.i0;
+        const float* r0 = slab_row(tab, f, d0, t.j0, g.pitch) + t.i0;
+        const float* r1 = slab_row(tab, f, d0, t.j0 + 1, g.pitch) + t.i0;
         a00 = __ldg(r0); a10 = __ldg(r0 + 1); a01 = __ldg(r1); a11 = __ldg(r1 + 1);
     } else {
         const float* r0 = d0 + (size_t)t.j0 * g.pitch + t.i0;

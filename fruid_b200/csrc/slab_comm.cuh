@@ -15,7 +15,7 @@
 
 namespace fruid {
 
-constexpr int SLAB_HALO = 12;       // rows kept of each neighbour: >= fused sweeps (10) + 2
+constexpr int SLAB_HALO = 22;       // rows kept of each neighbour: two blocks of 10 fused sweeps + 2
 constexpr int SLAB_MAX_T = 10;      // fused sweeps per launch allowed in slab mode
 constexpr int SLAB_MAX_RANKS = 8;
 constexpr size_t SLAB_FLAG_BYTES = 4096;
@@ -51,7 +51,7 @@ __device__ __forceinline__ bool spin_until(const int* flag, int e, int* err) {
             *err = 1;
             return false;
         }
-        __nanosleep(64);
+        __nanosleep(20);
     }
     return true;
 }
@@ -93,8 +93,16 @@ __global__ void k_slab_pull(const __grid_constant__ PullArgs A) {
         const size_t n4 = (size_t)j.rows * A.pitch / 4;
         const float4* src = reinterpret_cast<const float4*>(j.src);
         float4* dst = reinterpret_cast<float4*>(j.dst);
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
-            dst[i] = __ldcv(src + i);  // peer memory: bypass L1
+        const size_t stride = (size_t)gridDim.x * blockDim.x;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 4 * stride) {
+            float4 t[4];  // issue the peer loads (NVLink latency) back to back, then store
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (i + k * stride < n4) t[k] = __ldcv(src + i + k * stride);  // peer memory: bypass L1
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (i + k * stride < n4) dst[i + k * stride] = t[k];
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {

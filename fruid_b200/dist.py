@@ -12,7 +12,7 @@ import ctypes
 
 import numpy as np
 
-HALO = 12   # rows kept of each neighbour (csrc/slab_comm.cuh: SLAB_HALO)
+HALO = 22   # rows kept of each neighbour (csrc/slab_comm.cuh: SLAB_HALO)
 MAX_T = 10  # fused Jacobi sweeps per launch allowed in slab mode (SLAB_MAX_T)
 
 

@@ -124,7 +124,7 @@ int fruid_density_sync(fruid_density_t *d);
 void *fruid_density_stream(fruid_density_t *d);
 
 /* ---- Multi-GPU y-slabs: one process per GPU -----------------------------------
- * Rank `rank` of `world` (<= 8) owns global rows [y0, y1) of the w x gh field plus 12 halo rows
+ * Rank `rank` of `world` (<= 8) owns global rows [y0, y1) of the w x gh field plus 22 halo rows
  * of each neighbour.  After creation every rank exports a 64-byte CUDA IPC handle of its device
  * allocation, the ranks exchange them out of band (the Python host side uses torch.distributed),
  * and each rank attaches all peers.  step()/step_dev() then run the same operator sequence as
