@@ -89,11 +89,14 @@ class ClockSampler:
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, enabled: bool = True, period_s: float = 0.05):
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.period_s = period_s
         self._stop = threading.Event()
         self._thr = None
         try:
+            if not enabled:
+                raise RuntimeError("disabled")
             import pynvml
             pynvml.nvmlInit()
             self._nv = pynvml
@@ -116,7 +119,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(self.period_s)
 
     def __enter__(self):
         if self._nv:
@@ -387,23 +390,31 @@ def run_b200_multi(args, fb, dist, rank, world, local):
     for _ in range(args.warmup):
         scene_step()
     sim.sync(); den.sync()
-    torch.cuda.synchronize()
-    dist.barrier()
     n0 = fb.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    # NVML is sampled on rank 0 only and slowly: concurrent NVML queries from 8 processes serialise
+    # in the driver and stall kernel launches.  The sampler starts BEFORE the barrier so that every
+    # rank enters the timed region together.
+    with ClockSampler(local, enabled=(rank == 0), period_s=0.2) as clk:
         torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t_host = time.perf_counter()
         e0.record(stream)
         for _ in range(args.steps):
             scene_step()
         e1.record(stream)
+        t_enq = time.perf_counter() - t_host
         sim.sync(); den.sync()
         torch.cuda.synchronize()
     dist.barrier()
     launches = fb.launch_count() - n0
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    mine_ms = e0.elapsed_time(e1)
+    ms = torch.tensor([mine_ms], device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, (round(mine_ms / args.steps, 4), round(t_enq * 1e3 / args.steps, 4)))
     value = w * h * args.steps / (ms * 1e-3)
 
     # per-kernel timing pass (rank 0's view; includes the time spent waiting for peers)
@@ -458,7 +469,8 @@ def run_b200_multi(args, fb, dist, rank, world, local):
                              "peak": 6551.4, "unit": "GB/s", "frac": bytes_per_cell_step() * value / world / 1e9 / 6551.4,
                              "traffic": None, "note": "per-GPU algorithmic bytes (188+60K per cell-step) / time; see the "
                                                       "N=1 line for the dominant kernel"},
-                "cpu_baseline": None, "impl": "b200", "kernels_launches_ms_per_step_rank0": kernels_ms}
+                "cpu_baseline": None, "impl": "b200", "kernels_launches_ms_per_step_rank0": kernels_ms,
+                "per_rank_ms_per_step_gpu_and_host_enqueue": per_rank}
         print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -53,6 +53,8 @@ SIGNATURES = {
     "fruid_fluid_ipc_export": [_vp, _vp],
     "fruid_fluid_ipc_attach": [_vp, _i, _vp],
     "fruid_fluid_slab_rows": [_vp, ctypes.POINTER(_sz), ctypes.POINTER(_sz)],
+    "fruid_fluid_debug_exchange": [_vp, _i, _i],
+    "fruid_fluid_debug_barrier": [_vp, _i],
     "fruid_density_create_slab": [_sz, _sz, _i, _i, ctypes.POINTER(_vp)],
     "fruid_density_ipc_export": [_vp, _vp],
     "fruid_density_ipc_attach": [_vp, _i, _vp],

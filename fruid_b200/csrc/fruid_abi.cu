@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -236,9 +237,9 @@ static int op_add_source_diffuse(int b, float*& x, float* x0, float*& scratch, f
     return op_lin_solve(b, x, x0, scratch, g, a, c, iters, fused, st, false, true, dt, z_tmp);
 }
 
-// advect, src/lib.rs:84-126, for 1 or 2 fields sharing the back-trace.  `tab` (optional) says where
-// the rows of the gathered fields live when they are slab-decomposed; [ly0, ly1) are the local
-// rows to produce (default: every interior row).
+// advect, src/lib.rs:84-126, for 1 or 2 fields sharing the back-trace.  `tab` (slab mode) says where
+// the rows of the gathered fields live on the other ranks; d0[] must then be indexed by GLOBAL row
+// and [ly0, ly1) are the local rows to produce (default: every interior row).
 static int op_advect(int nf, float* const* d, const float* const* d0, const int* b, const float* u, const float* v,
                      const Geom& g, float dt, cudaStream_t st, const SlabTable* tab = nullptr, int ly0 = -1, int ly1 = -1) {
     const float dt0 = dt * (float)g.nx, dt1 = dt * (float)g.ny;
@@ -258,15 +259,19 @@ static int op_advect(int nf, float* const* d, const float* const* d0, const int*
     if (!multi) tab = &single;
     if (ly0 < 0) { ly0 = 1; ly1 = g.h - 1; }
     if (ly1 <= ly0) return 0;
-    const dim3 grid(((g.w + 3) / 4 + 31) / 32, (ly1 - ly0 + 7) / 8);
-    if (nf == 2 && multi)
-        LAUNCH("k_advect4x2", st, (k_advect4<2, true><<<grid, vec_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, *tab)));
-    else if (nf == 2)
-        LAUNCH("k_advect4x2", st, (k_advect4<2, false><<<grid, vec_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, *tab)));
-    else if (multi)
-        LAUNCH("k_advect4x1", st, (k_advect4<1, true><<<grid, vec_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, *tab)));
-    else
-        LAUNCH("k_advect4x1", st, (k_advect4<1, false><<<grid, vec_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, *tab)));
+    const dim3 grid1(((g.w + 3) / 4 + 31) / 32, (ly1 - ly0 + 7) / 8);
+    SlabTable T = *tab;
+    T.grid_x = (int)grid1.x;
+    if (multi) CU(cudaMemsetAsync(T.block_list, 0, sizeof(int), st));  // empty work list for pass 2
+#define FRUID_ADVECT(NF, PASS, name) \
+    LAUNCH(name, st, (k_advect4<NF, PASS><<<(PASS == 2 ? dim3(296) : grid1), vec_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, T)))
+    if (!multi) {
+        if (nf == 2) FRUID_ADVECT(2, 0, "k_advect4x2"); else FRUID_ADVECT(1, 0, "k_advect4x1");
+    } else {  // pass 1: cells whose taps are all local; pass 2: the rest, from the owners' memory
+        if (nf == 2) { FRUID_ADVECT(2, 1, "k_advect4x2"); FRUID_ADVECT(2, 2, "k_advect4x2_remote"); }
+        else { FRUID_ADVECT(1, 1, "k_advect4x1"); FRUID_ADVECT(1, 2, "k_advect4x1_remote"); }
+    }
+#undef FRUID_ADVECT
     return 0;
 }
 
@@ -325,6 +330,9 @@ struct SlabInfo {
     char* peer_base[SLAB_MAX_RANKS] = {nullptr};  // every rank's allocation as mapped here ([rank] = mine)
     int attached = 1;                    // how many of them are mapped (mine counts)
     int ev_pull = 0, ev_bar = 0;         // epochs of the last exchange / barrier
+    int ev_adv = 0;                      // epoch of the last advect (src_done / adv_done flags)
+    int* adv_block_flag = nullptr;       // per-block "has remote cells" marks of the two-pass advect
+    size_t adv_blocks = 0;
 };
 
 struct FieldSet {
@@ -387,6 +395,7 @@ struct FieldSet {
         for (int r = 0; r < slab.world; ++r)
             if (r != slab.rank && slab.peer_base[r]) cudaIpcCloseMemHandle(slab.peer_base[r]);
         if (base) cudaFree(base);
+        if (slab.adv_block_flag) cudaFree(slab.adv_block_flag);
         if (ev) cudaEventDestroy(ev);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -502,15 +511,47 @@ struct FieldSet {
         LAUNCH("k_slab_barrier", stream, (k_slab_barrier<<<1, 32, 0, stream>>>(A)));
         return 0;
     }
-    // Where the owners keep field `fp` (f = slot 0/1 of the advect gather table).
-    void fill_table(SlabTable& t, int f, const float* fp) const {
+    // "I have finished writing the fields the next advect gathers from" (which = 0) / "I have finished
+    // that advect" (which = 1): broadcast to every rank, nobody waits here.
+    int signal_all(int which) {
+        SignalArgs A{};
+        A.event = slab.ev_adv; A.me = slab.rank; A.world = slab.world; A.which = which; A.mine = flags(slab.rank);
+        for (int r = 0; r < slab.world; ++r) A.peer[r] = flags(r);
+        LAUNCH("k_slab_signal_all", stream, (k_slab_signal_all<<<1, 32, 0, stream>>>(A)));
+        return 0;
+    }
+    // Wait until every rank has signalled `which` for advect epoch `event` (before overwriting gathered fields).
+    int wait_all(int which, int event) {
+        if (!is_slab() || event <= 0) return 0;
+        SignalArgs A{};
+        A.event = event; A.me = slab.rank; A.world = slab.world; A.which = which; A.mine = flags(slab.rank);
+        LAUNCH("k_slab_wait_all", stream, (k_slab_wait_all<<<1, 32, 0, stream>>>(A)));
+        return 0;
+    }
+    // Gather table of the coming advect (epoch slab.ev_adv): where the owners keep field `fp`
+    // (f = slot 0/1), as pointers indexed by GLOBAL row; plus the flags of the two-pass scheme.
+    int fill_table(SlabTable& t, int f, const float* fp) {
         t.world = slab.world;
         t.me = slab.rank;
-        t.my_lo = slab.own0[slab.rank]; t.my_hi = slab.own0[slab.rank + 1]; t.my_row0 = slab.row0[slab.rank];
+        t.my_lo = slab.own0[slab.rank]; t.my_hi = slab.own0[slab.rank + 1];
         for (int r = 0; r <= slab.world; ++r) t.own0[r] = slab.own0[r];
         const int phys = phys_index(fp);
-        for (int r = 0; r < slab.world; ++r) { t.row0[r] = slab.row0[r]; t.base[f][r] = peer_field(r, phys); }
+        for (int r = 0; r < slab.world; ++r) t.base[f][r] = peer_field(r, phys) - (ptrdiff_t)slab.row0[r] * (ptrdiff_t)g.pitch;
+        const size_t blocks = (size_t)(((g.w + 3) / 4 + 31) / 32) * (size_t)((g.h + 7) / 8);
+        if (blocks > slab.adv_blocks) {
+            if (slab.adv_block_flag) CU(cudaFree(slab.adv_block_flag));
+            CU(cudaMalloc(&slab.adv_block_flag, (2 * blocks + 1) * sizeof(int)));  // flags, then the pass-2 work list
+            CU(cudaMemsetAsync(slab.adv_block_flag, 0, (2 * blocks + 1) * sizeof(int), stream));
+            slab.adv_blocks = blocks;
+        }
+        t.block_flag = slab.adv_block_flag;
+        t.block_list = slab.adv_block_flag + slab.adv_blocks;
+        t.src_done = flags(slab.rank)->src_done;
+        t.error = &flags(slab.rank)->error;
+        t.event = slab.ev_adv;
+        return 0;
     }
+    const float* global_rows(const float* fp) const { return fp - (ptrdiff_t)g.gy0 * (ptrdiff_t)g.pitch; }
 };
 
 struct fruid_fluid { FieldSet s; };    // buf: 0=u 1=v 2=u_prev 3=v_prev 4=scratch (lib.rs:247-253) 5=add_source temporary
@@ -553,19 +594,21 @@ static int op_vel_step_slab(FieldSet& S, float visc, float dt) {
     }
     TRY(S.exchange({u0, v0}));
     TRY(project_slab(S, u0, v0, u, v, T));                                             // lib.rs:199
-    TRY(S.barrier());                          // every rank has finished writing u0, v0
+    S.slab.ev_adv += 1;
+    TRY(S.signal_all(0));                      // my u0, v0 are final: owners' rows may be gathered
     {
         SlabTable tab{};
-        S.fill_table(tab, 0, u0);
-        S.fill_table(tab, 1, v0);
+        TRY(S.fill_table(tab, 0, u0));
+        TRY(S.fill_table(tab, 1, v0));
         float* d[2] = {u, v};
-        const float* d0[2] = {u0, v0};
+        const float* d0[2] = {S.global_rows(u0), S.global_rows(v0)};
         const int b[2] = {B_NEGX, B_NEGY};
         const int ly0 = std::max(S.own_lo(), 1 - g.gy0), ly1 = std::min(S.own_hi(), g.gh - 1 - g.gy0);
         TRY(op_advect(2, d, d0, b, u0, v0, g, dt, st, &tab, ly0, ly1));                // lib.rs:204-205
     }
-    TRY(S.barrier());                          // every rank has finished reading u0, v0
+    TRY(S.signal_all(1));                      // I have stopped reading everybody's u0, v0
     TRY(S.exchange({u, v}));
+    TRY(S.wait_all(1, S.slab.ev_adv));         // everybody has: project may overwrite u0, v0 (as p, div)
     return project_slab(S, u, v, u0, v0, T);                                           // lib.rs:207
 }
 
@@ -577,18 +620,20 @@ static int op_dens_step_slab(FieldSet& S, const float* u, const float* v, float 
     float *&x = S.buf[0], *&x0 = S.buf[1], *&s = S.buf[2];
     float* const s2 = S.buf[3];
     const float a = ((dt * diff) * (float)g.nx) * (float)g.ny, c = 1.0f + 4.0f * a;
+    TRY(S.wait_all(1, S.slab.ev_adv));         // everybody has finished the previous advect's reads of x0
     TRY(S.exchange({x, x0}));
     SlabSolve sd{SLAB_HALO, SLAB_HALO, 0, [&S](std::initializer_list<float*> f) { return S.exchange(f); }};
     TRY(op_lin_solve(B_POSITIVE, x0, x, s, g, a, c, S.iters, T, st, false, true, dt, s2, &sd));  // lib.rs:172,175
-    TRY(S.barrier());
+    S.slab.ev_adv += 1;
+    TRY(S.signal_all(0));                      // my x0 is final
     SlabTable tab{};
-    S.fill_table(tab, 0, x0);
+    TRY(S.fill_table(tab, 0, x0));
     float* d[1] = {x};
-    const float* d0[1] = {x0};
+    const float* d0[1] = {S.global_rows(x0)};
     const int b[1] = {B_POSITIVE};
     const int ly0 = std::max(S.own_lo(), 1 - g.gy0), ly1 = std::min(S.own_hi(), g.gh - 1 - g.gy0);
     TRY(op_advect(1, d, d0, b, u, v, g, dt, st, &tab, ly0, ly1));                       // lib.rs:178
-    return S.barrier();
+    return S.signal_all(1);                    // I have stopped reading everybody's x0
 }
 
 #define NEED(h) do { if (!(h)) return fail(FRUID_ERR_BAD_ARG, "null handle"); CU(cudaSetDevice((h)->s.device)); } while (0)
@@ -620,6 +665,24 @@ extern "C" int fruid_fluid_slab_rows(const fruid_fluid_t* f, size_t* y0, size_t*
     if (!f || !y0 || !y1) return fail(FRUID_ERR_BAD_ARG, "null pointer");
     *y0 = (size_t)f->s.slab.own0[f->s.slab.rank];
     *y1 = (size_t)f->s.slab.own0[f->s.slab.rank + 1];
+    return 0;
+}
+// Diagnostics: n back-to-back halo exchanges of `nfields` fields / n all-rank barriers.
+extern "C" int fruid_fluid_debug_exchange(fruid_fluid_t* f, int nfields, int n) {
+    NEED(f);
+    FieldSet& s = f->s;
+    TRY(s.need_peers());
+    for (int i = 0; i < n; ++i) {
+        if (nfields >= 4) TRY(s.exchange({s.buf[0], s.buf[1], s.buf[2], s.buf[3]}));
+        else if (nfields >= 2) TRY(s.exchange({s.buf[0], s.buf[1]}));
+        else TRY(s.exchange({s.buf[0]}));
+    }
+    return 0;
+}
+extern "C" int fruid_fluid_debug_barrier(fruid_fluid_t* f, int n) {
+    NEED(f);
+    TRY(f->s.need_peers());
+    for (int i = 0; i < n; ++i) TRY(f->s.barrier());
     return 0;
 }
 extern "C" int fruid_fluid_destroy(fruid_fluid_t* f) {

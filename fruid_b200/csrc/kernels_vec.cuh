@@ -7,6 +7,7 @@
 #pragma once
 #include "common.cuh"
 #include "kernels_basic.cuh"
+#include "slab_comm.cuh"
 
 namespace fruid {
 
@@ -132,49 +133,75 @@ __global__ void k_gradient4(float* __restrict__ u, float* __restrict__ v, const 
     store_row4_bnd(v, g, B_NEGY, gx0, gy, vn);
 }
 
-// Where the rows of a field live when it is y-slab decomposed over several GPUs: rank r holds
-// global rows [row0[r], row0[r] + rows[r]) ... owned rows [own0[r], own0[r+1]) at base[f][r]
-// (a peer-mapped pointer, NVLink).  A gather tap at global row gj reads the copy of its OWNER.
+// Where the rows of a field live when it is y-slab decomposed over several GPUs: rank r owns global
+// rows [own0[r], own0[r+1]).  base[f][r] is rank r's copy of gather field f (a peer-mapped pointer,
+// NVLink) SHIFTED so that it is indexed by GLOBAL row: row gj of rank r sits at base[f][r] + gj*pitch.
+// A gather tap at global row gj reads the copy of its OWNER.
 struct SlabTable {
-    int world;                 // 1 = single GPU (base[.][0] = local field, row0[0] = 0)
-    int me;                    // my rank
-    int my_lo, my_hi, my_row0; // my owned global rows [my_lo, my_hi) and the global row of my local row 0:
-                               // taps inside them use the local field pointer (no table lookup)
-    int own0[9];               // owned global rows of rank r: [own0[r], own0[r+1])
-    int row0[8];               // global row of local row 0 of rank r
-    const float* base[2][8];   // [field][rank]
+    int world;                 // 1 = single GPU
+    int me;
+    int my_lo, my_hi;          // my owned global rows [my_lo, my_hi): taps inside use the local pointer
+    int own0[9];
+    const float* base[2][8];   // [field][rank], global-row indexed
+    int* block_flag;           // [nblocks]: pass 1 marks blocks that still have remote cells ...
+    int* block_list;           // ... and queues them here: [0] = count, [1..] = block ids (pass 2's work list)
+    int grid_x;                // blocks per row of the pass-1 grid
+    const int* src_done;       // my SlabFlags::src_done[]: src_done[r] >= event <=> rank r's fields are final
+    int* error;
+    int event;
 };
-__device__ __noinline__ const float* slab_row_remote(const SlabTable& t, int f, int gj, size_t pitch) {
-    int r = 0;
-    while (r + 1 < t.world && gj >= t.own0[r + 1]) ++r;
-    return t.base[f][r] + (size_t)(gj - t.row0[r]) * pitch;
+__device__ __forceinline__ int slab_owner(const SlabTable& t, int gj) {
+    int r = 0;  // branch-free: number of slab cuts at or below gj
+#pragma unroll
+    for (int k = 1; k < 8; ++k) r += (k < t.world && gj >= t.own0[k]) ? 1 : 0;
+    return r;
 }
-__device__ __forceinline__ const float* slab_row(const SlabTable& t, int f, const float* local, int gj, size_t pitch) {
-    if (gj >= t.my_lo && gj < t.my_hi) return local + (size_t)(gj - t.my_row0) * pitch;
-    return slab_row_remote(t, f, gj, pitch);  // rare: the tap belongs to another rank (peer memory)
+// Row gj of gather field f as its owner holds it (local pointer for my own rows).
+__device__ __forceinline__ const float* slab_row(const SlabTable& t, int f, const float* d0, int gj, size_t pitch) {
+    const float* base = (gj >= t.my_lo && gj < t.my_hi) ? d0 : t.base[f][slab_owner(t, gj)];
+    return base + (size_t)gj * pitch;
 }
-template <bool MULTI>
-__device__ __forceinline__ float gather_slab(const SlabTable& tab, int f, const float* __restrict__ d0, const Geom& g,
-                                             const Trace& t) {
-    float a00, a01, a10, a11;
-    if (MULTI) {
-        const float* r0 = slab_row(tab, f, d0, t.j0, g.pitch) + t.i0;
-        const float* r1 = slab_row(tab, f, d0, t.j0 + 1, g.pitch) + t.i0;
-        a00 = __ldg(r0); a10 = __ldg(r0 + 1); a01 = __ldg(r1); a11 = __ldg(r1 + 1);
-    } else {
-        const float* r0 = d0 + (size_t)t.j0 * g.pitch + t.i0;
-        a00 = __ldg(r0); a10 = __ldg(r0 + 1); a01 = __ldg(r0 + g.pitch); a11 = __ldg(r0 + g.pitch + 1);
-    }
+// Bilinear gather of one cell from local rows.  d0 is indexed by global row (on one GPU: the field).
+__device__ __forceinline__ float gather_local(const float* __restrict__ d0, const Geom& g, const Trace& t) {
+    const float* r0 = d0 + (size_t)t.j0 * g.pitch + t.i0;
+    const float a00 = __ldg(r0), a10 = __ldg(r0 + 1), a01 = __ldg(r0 + g.pitch), a11 = __ldg(r0 + g.pitch + 1);
     return mixf(mixf(a00, a01, t.t1), mixf(a10, a11, t.t1), t.s1);
 }
+// Four cells whose tap rows may belong to other ranks: all sixteen addresses first, then all sixteen
+// loads back to back (each is an NVLink round trip; serialising them would cost ~16x the latency).
+__device__ __forceinline__ float4 gather_remote4(const SlabTable& tab, int f, const float* d0, const Geom& g, const Trace (&t)[4]) {
+    const float* p[4][2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        p[c][0] = slab_row(tab, f, d0, t[c].j0, g.pitch) + t[c].i0;
+        p[c][1] = slab_row(tab, f, d0, t[c].j0 + 1, g.pitch) + t[c].i0;
+    }
+    float a[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {  // peer memory: volatile loads, no stale L1 lines
+        a[c][0] = __ldcv(p[c][0]); a[c][1] = __ldcv(p[c][1]); a[c][2] = __ldcv(p[c][0] + 1); a[c][3] = __ldcv(p[c][1] + 1);
+    }
+    float r[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) r[c] = mixf(mixf(a[c][0], a[c][1], t[c].t1), mixf(a[c][2], a[c][3], t[c].t1), t[c].s1);
+    return make_float4(r[0], r[1], r[2], r[3]);
+}
 
-// advect (src/lib.rs:84-126) for NF fields sharing one back-trace, four cells per thread.
-// Output rows: local rows [ly0, ly1) (all interior rows on one GPU; the owned rows of a slab).
-template <int NF, bool MULTI>
-__global__ void k_advect4(AdvectArgs a, const float* __restrict__ u, const float* __restrict__ v, Geom g, float dt0,
-                          float dt1, float xmax, float ymax, int ly0, int ly1, const __grid_constant__ SlabTable tab) {
-    const int gx0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
-    const int ly = blockIdx.y * blockDim.y + threadIdx.y + ly0;
+// advect (src/lib.rs:84-126) for NF fields sharing one back-trace, four cells per thread; block
+// (bx, by) covers 128 columns x 8 rows.  Output rows: local rows [ly0, ly1) (all interior rows on one
+// GPU; the owned rows of a slab).  a.d0[f] must be indexed by GLOBAL row (slab mode: local pointer
+// minus gy0 rows).
+//   PASS 0: single GPU.
+//   PASS 1: slab, common case -- threads whose eight tap rows are all mine do the work exactly like
+//           PASS 0; the others only queue their block for pass 2.
+//   PASS 2: slab, queued blocks only -- the remaining threads gather from the OWNERS' memory over
+//           NVLink, after the owners have published their fields (src_done).
+template <int NF, int PASS>
+__device__ __forceinline__ void advect4_block(const AdvectArgs& a, const float* __restrict__ u, const float* __restrict__ v,
+                                              const Geom& g, float dt0, float dt1, float xmax, float ymax, int ly0, int ly1,
+                                              const SlabTable& tab, int bx, int by) {
+    const int gx0 = 4 * (bx * blockDim.x + threadIdx.x);
+    const int ly = by * blockDim.y + threadIdx.y + ly0;
     if (gx0 >= g.w || ly >= ly1) return;
     const int gy = ly + g.gy0;  // global row: the back-trace and the gather use global coordinates
     const size_t k = (size_t)ly * g.pitch + gx0;
@@ -184,14 +211,59 @@ __global__ void k_advect4(AdvectArgs a, const float* __restrict__ u, const float
     t[1] = backtrace(gx0 + 1, gy, uc.y, vc.y, dt0, dt1, xmax, ymax);
     t[2] = backtrace(gx0 + 2, gy, uc.z, vc.z, dt0, dt1, xmax, ymax);
     t[3] = backtrace(gx0 + 3, gy, uc.w, vc.w, dt0, dt1, xmax, ymax);
+    if (PASS != 0) {
+        const int jmin = min(min(t[0].j0, t[1].j0), min(t[2].j0, t[3].j0));
+        const int jmax = max(max(t[0].j0, t[1].j0), max(t[2].j0, t[3].j0));
+        const bool local = (jmin >= tab.my_lo) && (jmax + 1 < tab.my_hi);
+        if (PASS == 1 && !local) {  // the first thread to mark the block also queues it for pass 2
+            const int bid = by * tab.grid_x + bx;
+            if (atomicExch(&tab.block_flag[bid], 1) == 0) tab.block_list[1 + atomicAdd(&tab.block_list[0], 1)] = bid;
+            return;
+        }
+        if (PASS == 2 && local) return;  // done in pass 1
+        if (PASS == 2) {  // taps beyond the neighbours' rows (large displacement): wait for those owners too
+            const int r0 = slab_owner(tab, jmin), r1 = slab_owner(tab, jmax + 1);
+            for (int r = r0; r <= r1; ++r)
+                if (r < tab.me - 1 || r > tab.me + 1) spin_until(&tab.src_done[r], tab.event, tab.error);
+        }
+    }
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
         float4 r;
-        r.x = gather_slab<MULTI>(tab, f, a.d0[f], g, t[0]);
-        r.y = gather_slab<MULTI>(tab, f, a.d0[f], g, t[1]);
-        r.z = gather_slab<MULTI>(tab, f, a.d0[f], g, t[2]);
-        r.w = gather_slab<MULTI>(tab, f, a.d0[f], g, t[3]);
+        if (PASS != 2) {
+            r.x = gather_local(a.d0[f], g, t[0]);
+            r.y = gather_local(a.d0[f], g, t[1]);
+            r.z = gather_local(a.d0[f], g, t[2]);
+            r.w = gather_local(a.d0[f], g, t[3]);
+        } else {
+            r = gather_remote4(tab, f, a.d0[f], g, t);
+        }
         store_row4_bnd(a.d[f], g, a.b[f], gx0, ly, r);
+    }
+}
+
+// PASS 0 / 1: one block per 128 x 8 cells.  PASS 2: a small persistent grid walks the list of blocks
+// that pass 1 queued (typically the one or two block rows next to a slab cut).
+template <int NF, int PASS>
+__global__ void k_advect4(AdvectArgs a, const float* __restrict__ u, const float* __restrict__ v, Geom g, float dt0,
+                          float dt1, float xmax, float ymax, int ly0, int ly1, const __grid_constant__ SlabTable tab) {
+    if (PASS != 2) {
+        advect4_block<NF, PASS>(a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, tab, blockIdx.x, blockIdx.y);
+        return;
+    }
+    const int count = tab.block_list[0];
+    if (count == 0) return;
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        // One thread waits (system-scope acquire) for the two NEIGHBOUR owners on behalf of the block --
+        // a system fence per thread would serialise; farther owners are handled per thread.
+        if (tab.me > 0) spin_until(&tab.src_done[tab.me - 1], tab.event, tab.error);
+        if (tab.me + 1 < tab.world) spin_until(&tab.src_done[tab.me + 1], tab.event, tab.error);
+    }
+    __syncthreads();
+    for (int i = blockIdx.x; i < count; i += gridDim.x) {
+        const int bid = tab.block_list[1 + i];
+        if (threadIdx.x == 0 && threadIdx.y == 0) tab.block_flag[bid] = 0;
+        advect4_block<NF, 2>(a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, tab, bid % tab.grid_x, bid / tab.grid_x);
     }
 }
 

@@ -26,6 +26,8 @@ struct SlabFlags {
     int ready[SLAB_MAX_RANKS];     // ready[s]    >= e : rank s has produced everything up to event e
     int consumed[SLAB_MAX_RANKS];  // consumed[s] >= e : rank s has finished reading my rows for event e
     int bar[SLAB_MAX_RANKS];       // bar[s]      >= e : rank s has reached barrier e
+    int src_done[SLAB_MAX_RANKS];  // src_done[s] >= e : rank s has finished WRITING the fields advect e gathers from
+    int adv_done[SLAB_MAX_RANKS];  // adv_done[s] >= e : rank s has finished advect e (stopped READING those fields)
     int error;                     // set when a spin timed out
     int pull_done;                 // CTA counter of the running pull kernel (self-resetting)
 };
@@ -43,16 +45,24 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// Spin until *flag >= e (false on timeout).
+__device__ __forceinline__ int ld_relaxed_sys(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Spin until *flag >= e (false on timeout): relaxed system-scope polls, one acquire fence at the end.
 __device__ __forceinline__ bool spin_until(const int* flag, int e, int* err) {
-    const unsigned long long t0 = globaltimer_ns();
-    while (ld_acquire_sys(flag) < e) {
-        if (globaltimer_ns() - t0 > SPIN_TIMEOUT_NS) {
-            *err = 1;
-            return false;
+    if (ld_relaxed_sys(flag) < e) {
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned it = 0;
+        while (ld_relaxed_sys(flag) < e) {
+            if ((++it & 1023u) == 0 && globaltimer_ns() - t0 > SPIN_TIMEOUT_NS) {
+                *err = 1;
+                return false;
+            }
         }
-        __nanosleep(20);
     }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
     return true;
 }
 
@@ -81,7 +91,6 @@ __global__ void k_slab_pull(const __grid_constant__ PullArgs A) {
     __shared__ int s_ok;
     SlabFlags* mine = A.mine;
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
-        __threadfence_system();
         for (int d = 0; d < 2; ++d)
             if (A.nbr[d] >= 0) st_release_sys(&A.peer[d]->ready[A.me], A.event);
     }
@@ -118,6 +127,29 @@ __global__ void k_slab_pull(const __grid_constant__ PullArgs A) {
     }
 }
 
+// "Lazy" all-rank synchronisation around the peer gathers of advect: instead of two barriers,
+// every rank BROADCASTS an epoch (no waiting) when it has finished writing the gathered fields
+// (src_done) and when it has finished its advect (adv_done); a gathering thread waits only for the
+// OWNER of a remote tap (k_advect4 pass 2), and a rank waits for everybody's adv_done only right
+// before it overwrites the gathered fields -- by then the flags have long arrived.
+struct SignalArgs {
+    int event, me, world, which;   // which: 0 = src_done, 1 = adv_done
+    SlabFlags* mine;
+    SlabFlags* peer[SLAB_MAX_RANKS];
+};
+__global__ void k_slab_signal_all(const __grid_constant__ SignalArgs A) {
+    const int t = threadIdx.x;
+    if (t < A.world) {
+        int* flag = A.which == 0 ? &A.peer[t]->src_done[A.me] : &A.peer[t]->adv_done[A.me];
+        st_release_sys(flag, A.event);  // release: everything this stream wrote before is visible first
+    }
+}
+__global__ void k_slab_wait_all(const __grid_constant__ SignalArgs A) {
+    const int t = threadIdx.x;
+    if (t < A.world && t != A.me)
+        spin_until(A.which == 0 ? &A.mine->src_done[t] : &A.mine->adv_done[t], A.event, &A.mine->error);
+}
+
 struct BarrierArgs {
     int event, me, world;
     SlabFlags* mine;
@@ -127,7 +159,6 @@ struct BarrierArgs {
 __global__ void k_slab_barrier(const __grid_constant__ BarrierArgs A) {
     const int t = threadIdx.x;
     if (t < A.world && t != A.me) {
-        __threadfence_system();
         st_release_sys(&A.peer[t]->bar[A.me], A.event);
         spin_until(&A.mine->bar[t], A.event, &A.mine->error);
     }

@@ -136,6 +136,9 @@ int fruid_fluid_create_slab(size_t w, size_t gh, int rank, int world, fruid_flui
 int fruid_fluid_ipc_export(fruid_fluid_t *f, void *handle64);
 int fruid_fluid_ipc_attach(fruid_fluid_t *f, int peer_rank, const void *handle64);
 int fruid_fluid_slab_rows(const fruid_fluid_t *f, size_t *y0, size_t *y1);
+/* Diagnostics (latency of the slab primitives): n halo exchanges of nfields fields / n barriers. */
+int fruid_fluid_debug_exchange(fruid_fluid_t *f, int nfields, int n);
+int fruid_fluid_debug_barrier(fruid_fluid_t *f, int n);
 int fruid_density_create_slab(size_t w, size_t gh, int rank, int world, fruid_density_t **out);
 int fruid_density_ipc_export(fruid_density_t *d, void *handle64);
 int fruid_density_ipc_attach(fruid_density_t *d, int peer_rank, const void *handle64);
