@@ -354,6 +354,12 @@ struct FieldSet {
     int own_lo() const { return slab.own0[slab.rank] - slab.row0[slab.rank]; }
     int own_hi() const { return slab.own0[slab.rank + 1] - slab.row0[slab.rank]; }
     size_t peer_field_bytes(int r) const { return g.pitch * (size_t)slab.rows[r] * sizeof(float); }
+    size_t outbox_slot_bytes() const { return g.pitch * (size_t)SLAB_HALO * sizeof(float); }
+    // rank r's outbox slot for (event parity, field slot 0..3, direction 0 = towards rank-1, 1 = towards rank+1)
+    float* outbox(int r, int parity, int slot, int dir) const {
+        return (float*)(slab.peer_base[r] + SLAB_FLAG_BYTES + (size_t)n * peer_field_bytes(r) +
+                        (size_t)((parity * 4 + slot) * 2 + dir) * outbox_slot_bytes());
+    }
     int phys_index(const float* p) const { return (int)(((const char*)p - (base + SLAB_FLAG_BYTES)) / field_bytes); }
     float* peer_field(int r, int phys) const { return (float*)(slab.peer_base[r] + SLAB_FLAG_BYTES + (size_t)phys * peer_field_bytes(r)); }
     SlabFlags* flags(int r) const { return (SlabFlags*)slab.peer_base[r]; }
@@ -382,7 +388,8 @@ struct FieldSet {
         CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         field_bytes = g.pitch * (size_t)g.h * sizeof(float);
-        const size_t total = SLAB_FLAG_BYTES + (size_t)n * field_bytes;
+        // slab mode: outbox = 2 parities x 4 field slots x 2 directions x SLAB_HALO rows (halo exchange staging)
+        const size_t total = SLAB_FLAG_BYTES + (size_t)n * field_bytes + (world > 1 ? 16 * outbox_slot_bytes() : 0);
         CU(cudaMalloc(&base, total));
         CU(cudaMemsetAsync(base, 0, total, stream));  // Array2D::new zero-fills, lib.rs:218,257
         for (int i = 0; i < n; ++i) buf[i] = (float*)(base + SLAB_FLAG_BYTES + (size_t)i * field_bytes);
@@ -472,7 +479,7 @@ struct FieldSet {
         slab.attached += 1;
         return 0;
     }
-    // Halo exchange of up to 4 fields: pull SLAB_HALO rows from each neighbour's owned rows.
+    // Halo exchange of up to 4 fields: publish my boundary rows in my outbox, pull the neighbours'.
     int exchange(std::initializer_list<float*> fields) {
         if (!is_slab()) return 0;
         PullArgs A{};
@@ -482,25 +489,34 @@ struct FieldSet {
         A.nbr[1] = me + 1 < slab.world ? me + 1 : -1;
         A.mine = flags(me);
         for (int d = 0; d < 2; ++d) A.peer[d] = A.nbr[d] >= 0 ? flags(A.nbr[d]) : nullptr;
-        int nj = 0;
+        const int par = A.event & 1;
+        int nj = 0, slot = 0;
         for (float* fp : fields) {
-            const int phys = phys_index(fp);
             PullJob up{}, dn{};
-            if (A.nbr[0] >= 0) {  // my top halo rows = the last rows the upper neighbour owns
-                up.rows = slab.own0[me] - slab.row0[me];
+            if (A.nbr[0] >= 0) {
+                // the upper neighbour's bottom halo = my first owned rows; my top halo = its last owned rows,
+                // which it publishes in its "towards rank+1" slot
+                up.out_rows = slab.row0[me - 1] + slab.rows[me - 1] - slab.own0[me];
+                up.mine = fp + (size_t)own_lo() * g.pitch;
+                up.outbox = outbox(me, par, slot, 0);
+                up.in_rows = slab.own0[me] - slab.row0[me];
                 up.dst = fp;
-                up.src = peer_field(me - 1, phys) + (size_t)(slab.row0[me] - slab.row0[me - 1]) * g.pitch;
+                up.src = outbox(me - 1, par, slot, 1);
             }
-            if (A.nbr[1] >= 0) {  // my bottom halo rows = the first rows the lower neighbour owns
-                dn.rows = slab.row0[me] + slab.rows[me] - slab.own0[me + 1];
-                dn.dst = fp + (size_t)(slab.own0[me + 1] - slab.row0[me]) * g.pitch;
-                dn.src = peer_field(me + 1, phys) + (size_t)(slab.own0[me + 1] - slab.row0[me + 1]) * g.pitch;
+            if (A.nbr[1] >= 0) {
+                dn.out_rows = slab.own0[me + 1] - slab.row0[me + 1];
+                dn.mine = fp + (size_t)(own_hi() - dn.out_rows) * g.pitch;
+                dn.outbox = outbox(me, par, slot, 1);
+                dn.in_rows = slab.row0[me] + slab.rows[me] - slab.own0[me + 1];
+                dn.dst = fp + (size_t)own_hi() * g.pitch;
+                dn.src = outbox(me + 1, par, slot, 0);
             }
             A.job[nj++] = up;
             A.job[nj++] = dn;
+            ++slot;
         }
         A.njobs = nj;
-        LAUNCH("k_slab_pull", stream, (k_slab_pull<<<dim3(16, nj), 256, 0, stream>>>(A)));
+        LAUNCH("k_slab_pull", stream, (k_slab_pull<<<dim3(32, nj), 256, 0, stream>>>(A)));
         return 0;
     }
     int barrier() {

@@ -24,7 +24,6 @@ constexpr unsigned long long SPIN_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
 // Flag block at the start of every rank's allocation (written by peers, read locally).
 struct SlabFlags {
     int ready[SLAB_MAX_RANKS];     // ready[s]    >= e : rank s has produced everything up to event e
-    int consumed[SLAB_MAX_RANKS];  // consumed[s] >= e : rank s has finished reading my rows for event e
     int bar[SLAB_MAX_RANKS];       // bar[s]      >= e : rank s has reached barrier e
     int src_done[SLAB_MAX_RANKS];  // src_done[s] >= e : rank s has finished WRITING the fields advect e gathers from
     int adv_done[SLAB_MAX_RANKS];  // adv_done[s] >= e : rank s has finished advect e (stopped READING those fields)
@@ -66,13 +65,17 @@ __device__ __forceinline__ bool spin_until(const int* flag, int e, int* err) {
     return true;
 }
 
-struct PullJob {           // copy `rows` rows of `pitch` floats from a peer's field into my halo rows
-    const float* src;      // peer-mapped pointer to the first row to copy
-    float* dst;
-    int rows;
+// One direction of one field in a halo exchange: my boundary rows go to my OUTBOX (a staging area
+// in my own allocation that the neighbour reads), the neighbour's outbox rows come into my halo rows.
+struct PullJob {
+    const float* mine;     // first of my owned rows that the neighbour in this direction needs
+    float* outbox;         // my outbox slot for (this event's parity, field, direction)
+    const float* src;      // the neighbour's outbox slot holding MY halo rows (peer-mapped pointer)
+    float* dst;            // my halo rows
+    int out_rows, in_rows; // rows I publish / rows I receive (0 when there is no neighbour)
 };
 struct PullArgs {
-    PullJob job[8];        // up to 4 fields x 2 directions
+    PullJob job[8];        // up to 4 fields x 2 directions; job 2f = up (rank-1), 2f+1 = down (rank+1)
     int njobs;
     size_t pitch;
     int event;             // epoch of this exchange
@@ -82,49 +85,47 @@ struct PullArgs {
     SlabFlags* peer[2];    // neighbours' flag blocks (peer-mapped)
 };
 
-// One halo exchange event.  grid.x = CTAs per job, grid.y = njobs.
-//  1. announce that my rows are ready (stream order put my producing kernels before this launch),
-//  2. wait for the neighbours' announcements, pull their rows into my halo rows,
-//  3. the last CTA tells the neighbours that I am done reading and waits until they are done
-//     reading mine, so that whatever follows on this stream may overwrite the exchanged fields.
+__device__ __forceinline__ void copy_rows4(float4* dst, const float4* src, size_t n4, bool peer) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 4 * stride) {
+        float4 t[4];  // loads back to back (NVLink latency for peer rows), then the stores
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i + k * stride < n4) t[k] = peer ? __ldcv(src + i + k * stride) : src[i + k * stride];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i + k * stride < n4) dst[i + k * stride] = t[k];
+    }
+}
+
+// One halo exchange event, single handshake.  grid.x = CTAs per job, grid.y = njobs.
+//  A. every CTA copies its share of my boundary rows into my outbox; the last one to finish
+//     announces (release, system scope) that outbox[event & 1] is ready;
+//  B. every CTA waits for the neighbour's announcement and pulls its share of the neighbour's
+//     outbox rows into my halo rows.
+// No "done reading" handshake is needed: outbox[event & 1] is rewritten at event + 2, which I can
+// only reach after the neighbour announced event + 1, i.e. after its pull of this event completed.
 __global__ void k_slab_pull(const __grid_constant__ PullArgs A) {
     __shared__ int s_ok;
     SlabFlags* mine = A.mine;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
-        for (int d = 0; d < 2; ++d)
-            if (A.nbr[d] >= 0) st_release_sys(&A.peer[d]->ready[A.me], A.event);
-    }
     const PullJob j = A.job[blockIdx.y];
-    const int d = blockIdx.y & 1;  // jobs alternate up / down
-    if (threadIdx.x == 0) s_ok = (A.nbr[d] < 0) ? 0 : (spin_until(&mine->ready[A.nbr[d]], A.event, &mine->error) ? 1 : 0);
-    __syncthreads();
-    if (s_ok && j.rows > 0) {
-        const size_t n4 = (size_t)j.rows * A.pitch / 4;
-        const float4* src = reinterpret_cast<const float4*>(j.src);
-        float4* dst = reinterpret_cast<float4*>(j.dst);
-        const size_t stride = (size_t)gridDim.x * blockDim.x;
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 4 * stride) {
-            float4 t[4];  // issue the peer loads (NVLink latency) back to back, then store
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (i + k * stride < n4) t[k] = __ldcv(src + i + k * stride);  // peer memory: bypass L1
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (i + k * stride < n4) dst[i + k * stride] = t[k];
-        }
-    }
+    const int d = blockIdx.y & 1;
+    if (j.out_rows > 0)
+        copy_rows4(reinterpret_cast<float4*>(j.outbox), reinterpret_cast<const float4*>(j.mine), (size_t)j.out_rows * A.pitch / 4, false);
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        __threadfence();
         const int total = gridDim.x * gridDim.y;
         if (atomicAdd(&mine->pull_done, 1) == total - 1) {
             mine->pull_done = 0;
             for (int dd = 0; dd < 2; ++dd)
-                if (A.nbr[dd] >= 0) st_release_sys(&A.peer[dd]->consumed[A.me], A.event);
-            for (int dd = 0; dd < 2; ++dd)
-                if (A.nbr[dd] >= 0) spin_until(&mine->consumed[A.nbr[dd]], A.event, &mine->error);
+                if (A.nbr[dd] >= 0) st_release_sys(&A.peer[dd]->ready[A.me], A.event);
         }
+        s_ok = (A.nbr[d] < 0) ? 0 : (spin_until(&mine->ready[A.nbr[d]], A.event, &mine->error) ? 1 : 0);
     }
+    __syncthreads();
+    if (s_ok && j.in_rows > 0)
+        copy_rows4(reinterpret_cast<float4*>(j.dst), reinterpret_cast<const float4*>(j.src), (size_t)j.in_rows * A.pitch / 4, true);
 }
 
 // "Lazy" all-rank synchronisation around the peer gathers of advect: instead of two barriers,
