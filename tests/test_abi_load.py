@@ -52,3 +52,63 @@ def test_product_package_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "fruid_oracle" not in src, f
+
+
+def _sass():
+    import subprocess
+    import __graft_entry__
+    __graft_entry__.build()
+    from fruid_b200 import _lib
+    r = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    return r.stdout
+
+
+def test_no_fused_multiply_add_outside_division():
+    """Rust never contracts a*b+c.  ptxas 12.9 was seen fusing mul.rn.f32x2 + add.rn.f32x2
+    into FFMA2 even under -fmad=false, so the built library must not contain any; scalar FFMA may appear
+    only inside the IEEE division sequence (kernels that never divide must have none)."""
+    sass = _sass()
+    assert "FFMA2" not in sass
+    func, counts = None, {}
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            func = m.group(1)
+            counts[func] = 0
+        elif func and re.search(r"\bFFMA\b", line):
+            counts[func] += 1
+    assert any("k_jacobi_tile" in f for f in counts)
+    for f, n in counts.items():
+        divides = ("jacobi" in f or "serial_lin" in f)  # the only kernels with a true division by c
+        if not divides:
+            assert n == 0, f"{f} contains {n} FFMA"
+    # division-free specialisations of the tile kernel (MODE_POW2 = 1, MODE_ONE = 2, MODE_POISSON = 3)
+    for f, n in counts.items():
+        if re.search(r"k_jacobi_tileILi\d+ELi\d+ELi[123]E", f):
+            assert n == 0, f"{f} contains {n} FFMA"
+
+
+def test_sm100_native_instructions_present():
+    sass = _sass()
+    assert "UTMALDG" in sass      # TMA tile loads (cp.async.bulk.tensor)
+    assert "FADD2" in sass        # packed f32x2 arithmetic
+    assert "SYNCS" in sass        # mbarrier
+
+
+def test_cpp_mirror_compiles_links_and_fails_loudly_without_gpu(tmp_path):
+    import subprocess
+    import torch
+    import __graft_entry__
+    __graft_entry__.build()
+    from fruid_b200 import _lib
+    exe = tmp_path / "cpp_api_check"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-o", str(exe), os.path.join(ROOT, "tests", "cpp_api_check.cpp"),
+                    "-L" + libdir, "-lfruid_b200", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 3, r.stdout + r.stderr   # FRUID_ERR_CUDA surfaced as fruid::Error

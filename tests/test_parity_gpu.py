@@ -299,3 +299,23 @@ def test_config1_scale_short(fb, oracle_mod, w, h):
     fa, fo = _scene_fields(a), _scene_fields(b)
     for k in fa:
         assert_bits(fa[k], fo[k], k)
+
+
+def test_cpp_mirror_runs_a_step(fb, tmp_path):
+    """include/fruid.hpp (the C++ mirror of the crate API) against the same library."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(fb.LIB_PATH)
+    exe = tmp_path / "cpp_api_check"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-o", str(exe), os.path.join(root, "tests", "cpp_api_check.cpp"),
+                    "-L" + libdir, "-lfruid_b200", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+
+
+def test_launch_counter_counts_kernels(fb):
+    sim = fb.FluidSim(300, 200)
+    n0 = fb.launch_count()
+    sim.step(0.1, 0.0)
+    sim.sync()
+    assert fb.launch_count() - n0 == 13   # 2x2 diffuse blocks + 2x(div + 2 blocks + grad) + advect
