@@ -173,7 +173,7 @@ def run_reference(args):
         return
     w = args.size
     total = args.steps + args.warmup
-    rows = 1024 if total <= 8 else (512 if total <= 16 else 256)
+    rows = 1024 if total <= 8 else (512 if total <= 16 else (256 if total <= 40 else 128))
     rows = min(rows, w)
     value, sec = cpu_scene_steps(w, rows, args.steps, args.warmup)
     sample = (f"each step = 1 scene step (K={ITERS}, D=1) of the faithful-order C oracle on a {w}x{rows} grid "
@@ -247,7 +247,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     n0 = fb.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    with ClockSampler(local, period_s=0.01) as clk:
         torch.cuda.synchronize()
         e0.record(stream)
         for _ in range(args.steps):
@@ -479,7 +479,7 @@ def run_b200_multi(args, fb, dist, rank, world, local):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=4096)

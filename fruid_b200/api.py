@@ -31,7 +31,8 @@ class Array2D:
         self._w, self._h = width, height
         self._host = np.zeros((height, width), np.float32)
         # page-lock the mirror (fixed length for the object's life) so transfers run at PCIe rate
-        self._pinned = lib.fruid_host_register(self._host.ctypes.data, self._host.nbytes) == 0
+        self._host_ptr = self._host.ctypes.data
+        self._pinned = lib.fruid_host_register(self._host_ptr, self._host.nbytes) == 0
         self._stale = False   # device newer than host
         self._dirty = False   # host newer than device (whole field)
         self._cells = []      # pending single-cell writes (x, y, value)
@@ -39,7 +40,10 @@ class Array2D:
     def __del__(self):
         if getattr(self, "_pinned", False) and lib is not None:
             self._pinned = False
-            lib.fruid_host_unregister(self._host.ctypes.data)
+            try:
+                lib.fruid_host_unregister(self._host_ptr)
+            except Exception:  # interpreter shutdown
+                pass
 
     def width(self) -> int:
         return self._w

@@ -335,7 +335,29 @@ struct SlabInfo {
     size_t adv_blocks = 0;
 };
 
+// A captured CUDA graph of one step for fixed parameters.  The 13-16 launches of a step are
+// launch-latency bound on grids up to ~1024^2; replaying a graph removes the per-launch host cost.
+struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    float dt = 0.f, p = 0.f;       // dt and visc / diff
+    int iters = 0, fused = 0;
+    const void* a0 = nullptr;      // density: the velocity pointers the graph was captured with
+    const void* a1 = nullptr;
+    uint64_t kernels = 0;          // kernel launches inside the graph
+    int direct_steps = 0;          // steps run without a graph (the first one warms allocations and caches)
+    bool failed = false;           // capture did not work for these parameters: stay on direct launches
+    bool matches(float dt_, float p_, int it, int fu, const void* b0, const void* b1) const {
+        return dt == dt_ && p == p_ && iters == it && fused == fu && a0 == b0 && a1 == b1;
+    }
+    void reset() {
+        if (exec) cudaGraphExecDestroy(exec);
+        exec = nullptr; failed = false;
+    }
+};
+static bool g_graphs_enabled = true;
+
 struct FieldSet {
+    StepGraph graph;
     Geom g{};
     int n = 0;       // buffers allocated: user fields, then scratch (lib.rs:213,252), then the add_source temporary
     int n_user = 0;  // fields the crate API exposes
@@ -399,6 +421,7 @@ struct FieldSet {
     }
     void release() {
         if (stream) cudaStreamSynchronize(stream);
+        graph.reset();
         for (int r = 0; r < slab.world; ++r)
             if (r != slab.rank && slab.peer_base[r]) cudaIpcCloseMemHandle(slab.peer_base[r]);
         if (base) cudaFree(base);
@@ -652,6 +675,59 @@ static int op_dens_step_slab(FieldSet& S, const float* u, const float* v, float 
     return S.signal_all(1);                    // I have stopped reading everybody's x0
 }
 
+// Runs `body` (which enqueues one step on S.stream) either directly or as a replayed CUDA graph.
+// A graph is captured on the second step with given parameters (the first warms lazy allocations),
+// and only kept if the step left the buffer roles unchanged (an even number of launches per
+// lin_solve), because the graph bakes the pointers in.
+template <class Body>
+static int run_step_graphed(FieldSet& S, float dt, float p, const void* a0, const void* a1, Body body) {
+    StepGraph& G = S.graph;
+    const bool usable = g_graphs_enabled && !g_prof_on && !S.is_slab();
+    if (usable && G.exec && G.matches(dt, p, S.iters, S.fused, a0, a1)) {
+        CU(cudaGraphLaunch(G.exec, S.stream));
+        g_launches.fetch_add(G.kernels, std::memory_order_relaxed);
+        return 0;
+    }
+    if (!usable || G.direct_steps < 1 || (G.failed && G.matches(dt, p, S.iters, S.fused, a0, a1))) {
+        G.direct_steps += 1;
+        return body();
+    }
+    // capture
+    G.reset();
+    G.dt = dt; G.p = p; G.iters = S.iters; G.fused = S.fused; G.a0 = a0; G.a1 = a1;
+    float* before[6];
+    for (int i = 0; i < 6; ++i) before[i] = S.buf[i];
+    const uint64_t k0 = g_launches.load();
+    if (cudaStreamBeginCapture(S.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        G.failed = true;
+        return body();
+    }
+    const int r = body();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(S.stream, &graph);
+    const uint64_t nk = g_launches.load() - k0;
+    g_launches.fetch_sub(nk, std::memory_order_relaxed);  // nothing has run yet
+    bool same = true;
+    for (int i = 0; i < 6; ++i) same &= (before[i] == S.buf[i]);
+    if (r != 0 || e != cudaSuccess || !graph || !same ||
+        cudaGraphInstantiate(&G.exec, graph, nullptr, nullptr, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        for (int i = 0; i < 6; ++i) S.buf[i] = before[i];
+        G.exec = nullptr;
+        G.failed = true;
+        return body();  // the captured work was never launched: run the step directly
+    }
+    cudaGraphDestroy(graph);
+    G.kernels = nk;
+    CU(cudaGraphLaunch(G.exec, S.stream));
+    g_launches.fetch_add(nk, std::memory_order_relaxed);
+    return 0;
+}
+// Tuning / debugging knob: replay steps as CUDA graphs (default on).
+extern "C" int fruid_set_graphs_enabled(int on) { g_graphs_enabled = on != 0; return 0; }
+
 #define NEED(h) do { if (!(h)) return fail(FRUID_ERR_BAD_ARG, "null handle"); CU(cudaSetDevice((h)->s.device)); } while (0)
 
 extern "C" int fruid_fluid_create(size_t w, size_t h, fruid_fluid_t** out) {
@@ -722,7 +798,9 @@ extern "C" int fruid_fluid_step(fruid_fluid_t* f, float dt, float visc) {
     NEED(f);
     FieldSet& s = f->s;
     if (s.is_slab()) return op_vel_step_slab(s, visc, dt);
-    return op_vel_step(s.buf[0], s.buf[1], s.buf[2], s.buf[3], s.buf[4], s.buf[5], s.g, visc, dt, s.iters, s.fused, s.stream);
+    return run_step_graphed(s, dt, visc, nullptr, nullptr, [&]() {
+        return op_vel_step(s.buf[0], s.buf[1], s.buf[2], s.buf[3], s.buf[4], s.buf[5], s.g, visc, dt, s.iters, s.fused, s.stream);
+    });
 }
 extern "C" int fruid_fluid_step_n(fruid_fluid_t* f, float dt, float visc, int n) {
     NEED(f);
@@ -797,7 +875,9 @@ extern "C" int fruid_density_step_dev(fruid_density_t* d, fruid_fluid_t* vel, fl
     if (s.is_slab())
         TRY(op_dens_step_slab(s, vs.buf[0], vs.buf[1], diff, dt));
     else
-        TRY(op_dens_step(s.buf[0], s.buf[1], vs.buf[0], vs.buf[1], s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream));
+        TRY(run_step_graphed(s, dt, diff, vs.buf[0], vs.buf[1], [&]() {
+            return op_dens_step(s.buf[0], s.buf[1], vs.buf[0], vs.buf[1], s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream);
+        }));
     CU(cudaEventRecord(s.ev, s.stream));
     CU(cudaStreamWaitEvent(vs.stream, s.ev, 0));
     return 0;

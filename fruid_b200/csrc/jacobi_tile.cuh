@@ -498,6 +498,11 @@ static int* tile_sched_for(cudaStream_t st) {
     return p;
 }
 
+static inline int tiles_needed(int extent, int tile, int stride) {
+    if (extent <= tile) return 1;
+    return (extent - tile + stride - 1) / stride + 1;
+}
+
 static inline int jacobi_tile_max_T(int R, int NW) {
     const int th = R * NW;
     int H = (th < 128 ? th : 128) / 2 - 2;  // keep at least 4 output rows/cols per tile
@@ -505,9 +510,15 @@ static inline int jacobi_tile_max_T(int R, int NW) {
 }
 
 static inline int jacobi_tile_default_fused(const Geom& g, int iters) {
-    (void)g;
     int T = g_tile_default_T;
-    const int mx = jacobi_tile_max_T(g_tile_cfg.R, g_tile_cfg.NW);
+    const int R = g_tile_cfg.R, NW = g_tile_cfg.NW, TH = R * NW;
+    const int mx = jacobi_tile_max_T(R, NW);
+    // Small grids are launch-latency bound and leave most SMs idle anyway: when the tiling at the
+    // default depth cannot even give every SM one tile, fuse a whole 20-sweep solve per launch
+    // (more halo recompute on SMs that would otherwise idle, half the launches).
+    const int H = T + (T & 1);
+    const long tiles = (long)tiles_needed(g.w, 128, 128 - 2 * H) * tiles_needed(g.h, TH, TH - 2 * H);
+    if (tiles < 148 && g.gh == g.h) T = 20;
     if (T > mx) T = mx;
     if (T > iters) T = iters;
     return T < 1 ? 1 : T;
@@ -540,11 +551,6 @@ static int jacobi_tile_launch_cfg(const TileArgs& A, int mode, cudaStream_t st) 
     if (mode == MODE_POW2) return jacobi_tile_launch_mode<R, NW, MODE_POW2>(A, st);
     if (mode == MODE_POISSON) return jacobi_tile_launch_mode<R, NW, MODE_POISSON>(A, st);
     return jacobi_tile_launch_mode<R, NW, MODE_ONE>(A, st);
-}
-
-static inline int tiles_needed(int extent, int tile, int stride) {
-    if (extent <= tile) return 1;
-    return (extent - tile + stride - 1) / stride + 1;
 }
 
 #define FRUID_TILE_CONFIGS(X) X(8, 16) X(10, 16) X(6, 16) X(6, 20) X(7, 20) X(5, 24) X(4, 24) X(8, 12) X(4, 16)

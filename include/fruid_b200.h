@@ -70,6 +70,9 @@ const char *fruid_build_info(void);
  * is 128 x rows_per_warp*warps cells) and the default number of fused sweeps (0 = keep). */
 int fruid_set_tile_config(int rows_per_warp, int warps, int default_fused);
 
+/* Tuning knob: replay FluidSim::step / DensitySim::step as captured CUDA graphs (default 1). */
+int fruid_set_graphs_enabled(int on);
+
 /* Page-lock / unlock a caller-owned host array (e.g. the Vec<f32> inside an Array2D). */
 int fruid_host_register(void *p, size_t bytes);
 int fruid_host_unregister(void *p);

@@ -315,7 +315,12 @@ def test_cpp_mirror_runs_a_step(fb, tmp_path):
 
 def test_launch_counter_counts_kernels(fb):
     sim = fb.FluidSim(300, 200)
+    sim.set_fused_sweeps(10)
     n0 = fb.launch_count()
     sim.step(0.1, 0.0)
     sim.sync()
     assert fb.launch_count() - n0 == 13   # 2x2 diffuse blocks + 2x(div + 2 blocks + grad) + advect
+    sim.step(0.1, 0.0)                    # captured as a CUDA graph and replayed: same kernel count
+    sim.step(0.1, 0.0)
+    sim.sync()
+    assert fb.launch_count() - n0 == 39
