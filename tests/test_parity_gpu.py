@@ -324,3 +324,115 @@ def test_launch_counter_counts_kernels(fb):
     sim.step(0.1, 0.0)
     sim.sync()
     assert fb.launch_count() - n0 == 39
+
+
+# ---- BASELINE.json's full sizes ---------------------------------------------------------------
+def _scene_fields_big(n, seed_scale=1.0):
+    import bench
+    return bench.make_scene(n, n)
+
+
+def _run_handles(fb, n, sc, steps, visc, fused=None, iters=20):
+    L = fb._lib.lib
+    sim, den = fb.FluidSim(n, n), fb.DensitySim(n, n)
+    if fused is not None:
+        sim.set_fused_sweeps(fused)
+        den.set_fused_sweeps(fused)
+    sim.set_iterations(iters)
+    den.set_iterations(iters)
+    for name, field in (("u", 0), ("v", 1), ("u_prev", 2), ("v_prev", 3)):
+        fb._lib.check(L.fruid_fluid_upload(sim._h, field, fb._lib.ptr(sc[name])))
+    for name, field in (("dens", 0), ("dens_prev", 1)):
+        fb._lib.check(L.fruid_density_upload(den._h, field, fb._lib.ptr(sc[name])))
+    for _ in range(steps):
+        fb._lib.check(L.fruid_fluid_step(sim._h, 0.01, visc))
+        fb._lib.check(L.fruid_density_step_dev(den._h, sim._h, 0.01, visc))
+    out = []
+    for f in range(4):
+        a = np.empty((n, n), np.float32)
+        fb._lib.check(L.fruid_fluid_download(sim._h, f, fb._lib.ptr(a)))
+        out.append(a)
+    for f in range(2):
+        a = np.empty((n, n), np.float32)
+        fb._lib.check(L.fruid_density_download(den._h, f, fb._lib.ptr(a)))
+        out.append(a)
+    return out
+
+
+NAMES6 = ("u", "v", "u_prev", "v_prev", "dens", "dens_prev")
+
+
+@pytest.mark.parametrize("visc", [0.0, 1e-6])
+def test_full_size_4096_vs_oracle(fb, oracle_mod, visc):
+    """BASELINE.json configs[2] (4096 x 4096, K = 20): two scene steps of the bench scene, every field of the
+    CUDA run bit-identical to the CPU oracle (OpenMP traversal, itself bit-identical to the faithful order)."""
+    n = 4096
+    sc = _scene_fields_big(n)
+    got = _run_handles(fb, n, sc, 2, visc)
+    of, od = oracle_mod.Fluid(n, n), oracle_mod.Density(n, n)
+    of.u[:], of.v[:], of.u_prev[:], of.v_prev[:] = sc["u"], sc["v"], sc["u_prev"], sc["v_prev"]
+    od.dens[:], od.dens_prev[:] = sc["dens"], sc["dens_prev"]
+    for _ in range(2):
+        of.step(0.01, visc)
+        od.step((of.u, of.v), 0.01, visc)
+    for g, want, name in zip(got, (of.u, of.v, of.u_prev, of.v_prev, od.dens, od.dens_prev), NAMES6):
+        assert_bits(g, want, name)
+
+
+def test_full_size_fused_depth_and_tile_shape_do_not_change_results(fb):
+    """Size-independent property at 4096 x 4096: the result may not depend on how the sweeps are fused
+    (one per launch, 4, 10 or 20 per launch) nor on the tile shape."""
+    n = 4096
+    sc = _scene_fields_big(n)
+    ref = _run_handles(fb, n, sc, 1, 1e-6, fused=1)
+    L = fb._lib.lib
+    try:
+        for (r, nw, t) in ((8, 16, 10), (8, 16, 4), (8, 16, 20), (4, 16, 6), (6, 20, 10)):
+            fb._lib.check(L.fruid_set_tile_config(r, nw, 0))
+            got = _run_handles(fb, n, sc, 1, 1e-6, fused=t)
+            for g, want, name in zip(got, ref, NAMES6):
+                assert_bits(g, want, f"{name} (tile {r}x{nw}, T={t})")
+    finally:
+        fb._lib.check(L.fruid_set_tile_config(8, 16, 0))
+
+
+@pytest.mark.parametrize("iters", [40, 100, 200, 500])
+def test_iteration_sweep_config3(fb, oracle_mod, iters):
+    """BASELINE.json configs[3]: Jacobi-iteration sweep 20-500 (pressure-dominated regime), here on a
+    1024 x 512 grid so that the oracle finishes in seconds; one scene step, bit-exact."""
+    w, h = 1024, 512
+    import bench
+    sc = bench.make_scene(w, h)
+    L = fb._lib.lib
+    sim, den = fb.FluidSim(w, h), fb.DensitySim(w, h)
+    sim.set_iterations(iters)
+    den.set_iterations(iters)
+    of, od = oracle_mod.Fluid(w, h, iters=iters), oracle_mod.Density(w, h, iters=iters)
+    for name, field in (("u", 0), ("v", 1), ("u_prev", 2), ("v_prev", 3)):
+        fb._lib.check(L.fruid_fluid_upload(sim._h, field, fb._lib.ptr(sc[name])))
+    for name, field in (("dens", 0), ("dens_prev", 1)):
+        fb._lib.check(L.fruid_density_upload(den._h, field, fb._lib.ptr(sc[name])))
+    of.u[:], of.v[:], of.u_prev[:], of.v_prev[:] = sc["u"], sc["v"], sc["u_prev"], sc["v_prev"]
+    od.dens[:], od.dens_prev[:] = sc["dens"], sc["dens_prev"]
+    fb._lib.check(L.fruid_fluid_step(sim._h, 0.01, 1e-6))
+    fb._lib.check(L.fruid_density_step_dev(den._h, sim._h, 0.01, 1e-6))
+    of.step(0.01, 1e-6)
+    od.step((of.u, of.v), 0.01, 1e-6)
+    got = _read_fluid(fb, sim, w, h)
+    for g, want, name in zip(got, (of.u, of.v, of.u_prev, of.v_prev), NAMES6):
+        assert_bits(g, want, name)
+    a = np.empty((h, w), np.float32)
+    fb._lib.check(L.fruid_density_download(den._h, 0, fb._lib.ptr(a)))
+    assert_bits(a, od.dens, "dens")
+
+
+def test_x_mirror_symmetry_of_the_pressure_solve_at_full_size(fb):
+    """Property that needs no oracle: the 5-point sum ((l + r) + u) + d is symmetric under x -> w-1-x
+    (l + r == r + l exactly), so lin_solve commutes with an x flip bit for bit at any size."""
+    w, h = 4096, 1024
+    rng = np.random.default_rng(21)
+    x, x0, s = rand_field(rng, w, h), rand_field(rng, w, h), np.zeros((h, w), np.float32)
+    xf, x0f, sf = np.ascontiguousarray(x[:, ::-1]), np.ascontiguousarray(x0[:, ::-1]), s.copy()
+    fb.ops.lin_solve(POS, x, x0, s, 1.0, 4.0, 20, 0)
+    fb.ops.lin_solve(POS, xf, x0f, sf, 1.0, 4.0, 20, 0)
+    assert_bits(x, xf[:, ::-1], "flip")
