@@ -318,10 +318,12 @@ def run_b200(args):
 
 
 def run_e2e(args, fb, torch, sc, w, h):
-    """Scene step through the C ABI with HOST buffers (what the Rust shim's step() does when the
-    caller has rewritten its sources): every step uploads the three source fields (u_prev, v_prev,
-    dens_prev) from page-locked host arrays, runs FluidSim::step + DensitySim::step, and downloads
-    the resulting density to the host.  Wall clock over n steps, synchronised on both sides."""
+    """Scene step through the C ABI with HOST buffers: every step the three source fields (u_prev, v_prev,
+    dens_prev) come from page-locked host arrays (h2d) and the resulting density goes back to a host array
+    (d2h).  The transfers use the ABI's asynchronous variants (fruid_*_upload_async / _download_async): the
+    sources of step i+1 travel while step i computes and the density of step i travels while step i+1
+    computes.  Wall clock over n steps including every copy, synchronised on both sides; the serial
+    (blocking upload / step / download) figure is reported beside it."""
     from fruid_b200 import _lib
     L = _lib.lib
     sim, den = fb.FluidSim(w, h), fb.DensitySim(w, h)
@@ -331,35 +333,58 @@ def run_e2e(args, fb, torch, sc, w, h):
     for name, field in (("u", 0), ("v", 1)):
         _lib.check(L.fruid_fluid_upload(sim._h, field, _lib.ptr(sc[name])))
     _lib.check(L.fruid_density_upload(den._h, 0, _lib.ptr(sc["dens"])))
-    host = {k: np.ascontiguousarray(sc[k]) for k in ("u_prev", "v_prev", "dens_prev")}
-    out = np.empty((h, w), np.float32)
-    pinned = [a for a in (*host.values(), out) if L.fruid_host_register(a.ctypes.data, a.nbytes) == 0]
+    # two sets of host source arrays and two result arrays (what a double-buffering caller keeps)
+    host = [{k: np.ascontiguousarray(sc[k]).copy() for k in ("u_prev", "v_prev", "dens_prev")} for _ in range(2)]
+    out = [np.empty((h, w), np.float32) for _ in range(2)]
+    arrays = [a for hs in host for a in hs.values()] + out
+    pinned = [a for a in arrays if L.fruid_host_register(a.ctypes.data, a.nbytes) == 0]
     nbytes = w * h * 4
 
-    def step():
-        _lib.check(L.fruid_fluid_upload(sim._h, _lib.U_PREV, _lib.ptr(host["u_prev"])))      # h2d
-        _lib.check(L.fruid_fluid_upload(sim._h, _lib.V_PREV, _lib.ptr(host["v_prev"])))      # h2d
-        _lib.check(L.fruid_density_upload(den._h, _lib.DENS_PREV, _lib.ptr(host["dens_prev"])))  # h2d
-        _lib.check(L.fruid_fluid_step(sim._h, DT, VISC))
-        _lib.check(L.fruid_density_step_dev(den._h, sim._h, DT, DIFF))
-        _lib.check(L.fruid_density_download(den._h, _lib.DENS, _lib.ptr(out)))              # d2h (blocks)
+    def push(i):
+        hs = host[i & 1]
+        _lib.check(L.fruid_fluid_upload_async(sim._h, _lib.U_PREV, _lib.ptr(hs["u_prev"])))
+        _lib.check(L.fruid_fluid_upload_async(sim._h, _lib.V_PREV, _lib.ptr(hs["v_prev"])))
+        _lib.check(L.fruid_density_upload_async(den._h, _lib.DENS_PREV, _lib.ptr(hs["dens_prev"])))
 
-    for _ in range(2):
-        step()
-    torch.cuda.synchronize()
-    n = max(1, min(args.steps, 10))
-    t0 = time.perf_counter()
-    for _ in range(n):
-        step()
-    torch.cuda.synchronize()
-    sec = time.perf_counter() - t0
-    ok = bool(np.isfinite(out[:: max(1, h // 64), :: max(1, w // 64)]).all())
+    def pipelined(n):
+        push(0)
+        for i in range(n):
+            _lib.check(L.fruid_fluid_step(sim._h, DT, VISC))              # consumes the staged sources
+            _lib.check(L.fruid_density_step_dev(den._h, sim._h, DT, DIFF))
+            if i + 1 < n:
+                push(i + 1)                                                # h2d behind step i's kernels
+            _lib.check(L.fruid_density_download_async(den._h, _lib.DENS, _lib.ptr(out[i & 1])))  # d2h behind step i+1
+        _lib.check(L.fruid_fluid_sync(sim._h))
+        _lib.check(L.fruid_density_sync(den._h))
+
+    def serial(n):
+        for i in range(n):
+            hs = host[i & 1]
+            _lib.check(L.fruid_fluid_upload(sim._h, _lib.U_PREV, _lib.ptr(hs["u_prev"])))
+            _lib.check(L.fruid_fluid_upload(sim._h, _lib.V_PREV, _lib.ptr(hs["v_prev"])))
+            _lib.check(L.fruid_density_upload(den._h, _lib.DENS_PREV, _lib.ptr(hs["dens_prev"])))
+            _lib.check(L.fruid_fluid_step(sim._h, DT, VISC))
+            _lib.check(L.fruid_density_step_dev(den._h, sim._h, DT, DIFF))
+            _lib.check(L.fruid_density_download(den._h, _lib.DENS, _lib.ptr(out[i & 1])))
+
+    n = max(2, min(args.steps, 10))
+    res = {}
+    for name, fn in (("pipelined", pipelined), ("serial", serial)):
+        fn(2)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn(n)
+        torch.cuda.synchronize()
+        res[name] = w * h * n / (time.perf_counter() - t0)
+    ok = bool(np.isfinite(out[(n - 1) & 1][:: max(1, h // 64), :: max(1, w // 64)]).all())
     for a in pinned:
         L.fruid_host_unregister(a.ctypes.data)
-    return {"value": w * h * n / sec, "unit": "cell-steps/s", "h2d_bytes_per_step": 3 * nbytes,
-            "d2h_bytes_per_step": nbytes, "steps": n, "finite": ok, "pinned_host": len(pinned) == 4,
-            "note": "per step: h2d of the u_prev, v_prev and dens_prev source fields, FluidSim::step + "
-                    "DensitySim::step, d2h of density(); through the C ABI with host buffers"}
+    return {"value": res["pipelined"], "unit": "cell-steps/s", "h2d_bytes_per_step": 3 * nbytes,
+            "d2h_bytes_per_step": nbytes, "steps": n, "finite": ok, "pinned_host": len(pinned) == len(arrays),
+            "serial_value": res["serial"],
+            "note": "per step: h2d of the u_prev, v_prev and dens_prev source fields, FluidSim::step + DensitySim::step, "
+                    "d2h of density(); C ABI with page-locked host buffers; value = asynchronous (overlapped) transfers, "
+                    "serial_value = blocking upload/step/download"}
 
 
 def run_b200_multi(args, fb, dist, rank, world, local):

@@ -64,6 +64,10 @@ SIGNATURES = {
     "fruid_fluid_height": [_vp],
     "fruid_fluid_upload": [_vp, _i, _vp],
     "fruid_fluid_download": [_vp, _i, _vp],
+    "fruid_fluid_upload_async": [_vp, _i, _vp],
+    "fruid_fluid_download_async": [_vp, _i, _vp],
+    "fruid_density_upload_async": [_vp, _i, _vp],
+    "fruid_density_download_async": [_vp, _i, _vp],
     "fruid_fluid_inject": [_vp, _i, _sz, _sz, _f],
     "fruid_fluid_set_iterations": [_vp, _i],
     "fruid_fluid_set_fused_sweeps": [_vp, _i],

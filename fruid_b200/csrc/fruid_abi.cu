@@ -366,6 +366,15 @@ struct FieldSet {
     size_t field_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev = nullptr;
+    // Asynchronous transfers (pinned host memory): a copy stream, per-field upload staging buffers
+    // and one download snapshot, so that PCIe traffic overlaps the kernels of the neighbouring steps.
+    cudaStream_t copy_stream = nullptr;
+    float* up_stage[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t up_ev[4] = {nullptr, nullptr, nullptr, nullptr};      // staging buffer filled (copy stream)
+    cudaEvent_t up_used[4] = {nullptr, nullptr, nullptr, nullptr};    // staging buffer consumed (compute stream)
+    bool up_pending[4] = {false, false, false, false};
+    float* dl_stage = nullptr;
+    cudaEvent_t dl_snap = nullptr, dl_done = nullptr;                 // snapshot taken (compute) / downloaded (copy)
     int iters = 20;  // src/lib.rs:52
     int fused = 0;   // 0 = library default
     int device = 0;
@@ -424,6 +433,16 @@ struct FieldSet {
         graph.reset();
         for (int r = 0; r < slab.world; ++r)
             if (r != slab.rank && slab.peer_base[r]) cudaIpcCloseMemHandle(slab.peer_base[r]);
+        if (copy_stream) cudaStreamSynchronize(copy_stream);
+        for (int i = 0; i < 4; ++i) {
+            if (up_stage[i]) cudaFree(up_stage[i]);
+            if (up_ev[i]) cudaEventDestroy(up_ev[i]);
+            if (up_used[i]) cudaEventDestroy(up_used[i]);
+        }
+        if (dl_stage) cudaFree(dl_stage);
+        if (dl_snap) cudaEventDestroy(dl_snap);
+        if (dl_done) cudaEventDestroy(dl_done);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (base) cudaFree(base);
         if (slab.adv_block_flag) cudaFree(slab.adv_block_flag);
         if (ev) cudaEventDestroy(ev);
@@ -443,6 +462,68 @@ struct FieldSet {
                              (size_t)g.w * sizeof(float), (size_t)(own_hi() - own_lo()), cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
         return check_peer_error();
+    }
+    int ensure_copy_stream() {
+        if (!copy_stream) CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        return 0;
+    }
+    // Enqueue host -> staging on the copy stream; the next step() moves the staged rows into the field.
+    // The host array must be page-locked (fruid_host_register) and stay untouched until that step.
+    int upload_async(int field, const float* host) {
+        if (field < 0 || field >= n_user || !host) return fail(FRUID_ERR_BAD_ARG, "bad field %d or null host pointer", field);
+        TRY(ensure_copy_stream());
+        const size_t rows = (size_t)(own_hi() - own_lo());
+        if (!up_stage[field]) {
+            CU(cudaMalloc(&up_stage[field], g.pitch * rows * sizeof(float)));
+            CU(cudaEventCreateWithFlags(&up_ev[field], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&up_used[field], cudaEventDisableTiming));
+        } else {
+            CU(cudaStreamWaitEvent(copy_stream, up_used[field], 0));  // previous staged upload has been consumed
+        }
+        CU(cudaMemcpy2DAsync(up_stage[field], g.pitch * sizeof(float), host, (size_t)g.w * sizeof(float),
+                             (size_t)g.w * sizeof(float), rows, cudaMemcpyHostToDevice, copy_stream));
+        CU(cudaEventRecord(up_ev[field], copy_stream));
+        up_pending[field] = true;
+        return 0;
+    }
+    // Called at the start of a step: staged uploads become the fields' contents (device-to-device).
+    int consume_uploads() {
+        for (int f = 0; f < 4; ++f) {
+            if (!up_pending[f]) continue;
+            CU(cudaStreamWaitEvent(stream, up_ev[f], 0));
+            const size_t rows = (size_t)(own_hi() - own_lo());
+            CU(cudaMemcpyAsync(buf[f] + (size_t)own_lo() * g.pitch, up_stage[f], g.pitch * rows * sizeof(float),
+                               cudaMemcpyDeviceToDevice, stream));
+            CU(cudaEventRecord(up_used[f], stream));
+            up_pending[f] = false;
+        }
+        return 0;
+    }
+    // Snapshot the field on the compute stream, then device -> host on the copy stream (overlaps the
+    // next step).  The host array is valid after sync_copies().
+    int download_async(int field, float* host) {
+        if (field < 0 || field >= n_user || !host) return fail(FRUID_ERR_BAD_ARG, "bad field %d or null host pointer", field);
+        TRY(ensure_copy_stream());
+        const size_t rows = (size_t)(own_hi() - own_lo());
+        if (!dl_stage) {
+            CU(cudaMalloc(&dl_stage, g.pitch * rows * sizeof(float)));
+            CU(cudaEventCreateWithFlags(&dl_snap, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&dl_done, cudaEventDisableTiming));
+        } else {
+            CU(cudaStreamWaitEvent(stream, dl_done, 0));  // previous download has left the snapshot buffer
+        }
+        CU(cudaMemcpyAsync(dl_stage, buf[field] + (size_t)own_lo() * g.pitch, g.pitch * rows * sizeof(float),
+                           cudaMemcpyDeviceToDevice, stream));
+        CU(cudaEventRecord(dl_snap, stream));
+        CU(cudaStreamWaitEvent(copy_stream, dl_snap, 0));
+        CU(cudaMemcpy2DAsync(host, (size_t)g.w * sizeof(float), dl_stage, g.pitch * sizeof(float), (size_t)g.w * sizeof(float),
+                             rows, cudaMemcpyDeviceToHost, copy_stream));
+        CU(cudaEventRecord(dl_done, copy_stream));
+        return 0;
+    }
+    int sync_copies() {
+        if (copy_stream) CU(cudaStreamSynchronize(copy_stream));
+        return 0;
     }
     // (x, y) are GLOBAL cell coordinates; ranks that do not own row y ignore the write (their
     // halo copy is refreshed from the owner at the start of the next step).
@@ -791,12 +872,15 @@ extern "C" int fruid_fluid_download(fruid_fluid_t* f, int field, float* host) {
     NEED(f);
     return f->s.download(field, host);
 }
+extern "C" int fruid_fluid_upload_async(fruid_fluid_t* f, int field, const float* host) { NEED(f); return f->s.upload_async(field, host); }
+extern "C" int fruid_fluid_download_async(fruid_fluid_t* f, int field, float* host) { NEED(f); return f->s.download_async(field, host); }
 extern "C" int fruid_fluid_inject(fruid_fluid_t* f, int field, size_t x, size_t y, float val) { NEED(f); return f->s.inject(field, x, y, val); }
 extern "C" int fruid_fluid_set_iterations(fruid_fluid_t* f, int k) { NEED(f); return f->s.set_iters(k); }
 extern "C" int fruid_fluid_set_fused_sweeps(fruid_fluid_t* f, int t) { NEED(f); return f->s.set_fused(t); }
 extern "C" int fruid_fluid_step(fruid_fluid_t* f, float dt, float visc) {
     NEED(f);
     FieldSet& s = f->s;
+    TRY(s.consume_uploads());
     if (s.is_slab()) return op_vel_step_slab(s, visc, dt);
     return run_step_graphed(s, dt, visc, nullptr, nullptr, [&]() {
         return op_vel_step(s.buf[0], s.buf[1], s.buf[2], s.buf[3], s.buf[4], s.buf[5], s.g, visc, dt, s.iters, s.fused, s.stream);
@@ -809,7 +893,7 @@ extern "C" int fruid_fluid_step_n(fruid_fluid_t* f, float dt, float visc, int n)
     return 0;
 }
 extern "C" void* fruid_fluid_stream(fruid_fluid_t* f) { return f ? (void*)f->s.stream : nullptr; }
-extern "C" int fruid_fluid_sync(fruid_fluid_t* f) { NEED(f); CU(cudaStreamSynchronize(f->s.stream)); CU(cudaGetLastError()); return f->s.check_peer_error(); }
+extern "C" int fruid_fluid_sync(fruid_fluid_t* f) { NEED(f); CU(cudaStreamSynchronize(f->s.stream)); TRY(f->s.sync_copies()); CU(cudaGetLastError()); return f->s.check_peer_error(); }
 
 extern "C" int fruid_density_create(size_t w, size_t h, fruid_density_t** out) {
     if (!out) return fail(FRUID_ERR_BAD_ARG, "null out pointer");
@@ -845,6 +929,8 @@ extern "C" int fruid_density_download(fruid_density_t* d, int field, float* host
     NEED(d);
     return d->s.download(field, host);
 }
+extern "C" int fruid_density_upload_async(fruid_density_t* d, int field, const float* host) { NEED(d); return d->s.upload_async(field, host); }
+extern "C" int fruid_density_download_async(fruid_density_t* d, int field, float* host) { NEED(d); return d->s.download_async(field, host); }
 extern "C" int fruid_density_inject(fruid_density_t* d, int field, size_t x, size_t y, float val) { NEED(d); return d->s.inject(field, x, y, val); }
 extern "C" int fruid_density_fill(fruid_density_t* d, int field, float val) {
     NEED(d);
@@ -867,6 +953,7 @@ extern "C" int fruid_density_step_dev(fruid_density_t* d, fruid_fluid_t* vel, fl
     if (vs.g.w != s.g.w || vs.g.gh != s.g.gh)
         return fail(FRUID_ERR_SIZE_MISMATCH, "density %dx%d vs velocity %dx%d", s.g.w, s.g.gh, vs.g.w, vs.g.gh);
     if (vs.device != s.device) return fail(FRUID_ERR_BAD_ARG, "density and velocity live on different devices");
+    TRY(s.consume_uploads());
     // u,v are produced on vel's stream and consumed on ours; order both ways.
     CU(cudaEventRecord(vs.ev, vs.stream));
     CU(cudaStreamWaitEvent(s.stream, vs.ev, 0));
@@ -902,7 +989,7 @@ extern "C" int fruid_density_step_host(fruid_density_t* d, const float* u, const
     return 0;
 }
 extern "C" void* fruid_density_stream(fruid_density_t* d) { return d ? (void*)d->s.stream : nullptr; }
-extern "C" int fruid_density_sync(fruid_density_t* d) { NEED(d); CU(cudaStreamSynchronize(d->s.stream)); CU(cudaGetLastError()); return d->s.check_peer_error(); }
+extern "C" int fruid_density_sync(fruid_density_t* d) { NEED(d); CU(cudaStreamSynchronize(d->s.stream)); TRY(d->s.sync_copies()); CU(cudaGetLastError()); return d->s.check_peer_error(); }
 
 // Page-lock caller-owned host arrays (the Vec<f32> inside an Array2D has a fixed length for
 // the object's life) so uploads/downloads run at full PCIe rate.

@@ -94,6 +94,12 @@ size_t fruid_fluid_height(const fruid_fluid_t *f);
 /* Host <-> device copies of one field (dense w*h floats). */
 int fruid_fluid_upload(fruid_fluid_t *f, int field, const float *host);
 int fruid_fluid_download(fruid_fluid_t *f, int field, float *host);
+/* Asynchronous transfers for page-locked host arrays (fruid_host_register): upload_async stages the
+ * field on a copy stream -- it takes effect at the start of the NEXT step() and overlaps the kernels
+ * already enqueued; download_async snapshots the field in stream order and copies it out while later
+ * steps run.  The host array must stay untouched (upload) / is valid (download) after fruid_*_sync(). */
+int fruid_fluid_upload_async(fruid_fluid_t *f, int field, const float *host);
+int fruid_fluid_download_async(fruid_fluid_t *f, int field, float *host);
 /* `u[pos] = val` through uv_mut(), src/main.rs:98-102, without a full upload. */
 int fruid_fluid_inject(fruid_fluid_t *f, int field, size_t x, size_t y, float val);
 /* Sweeps per lin_solve; the reference hard-codes 20 (src/lib.rs:52).  Even only. */
@@ -113,6 +119,8 @@ int fruid_density_create(size_t w, size_t h, fruid_density_t **out);
 int fruid_density_destroy(fruid_density_t *d);
 int fruid_density_upload(fruid_density_t *d, int field, const float *host);
 int fruid_density_download(fruid_density_t *d, int field, float *host);
+int fruid_density_upload_async(fruid_density_t *d, int field, const float *host);
+int fruid_density_download_async(fruid_density_t *d, int field, float *host);
 int fruid_density_inject(fruid_density_t *d, int field, size_t x, size_t y, float val);
 /* `density_mut().data_mut().fill(v)`, src/main.rs:105-108. */
 int fruid_density_fill(fruid_density_t *d, int field, float val);

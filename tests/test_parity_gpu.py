@@ -436,3 +436,46 @@ def test_x_mirror_symmetry_of_the_pressure_solve_at_full_size(fb):
     fb.ops.lin_solve(POS, x, x0, s, 1.0, 4.0, 20, 0)
     fb.ops.lin_solve(POS, xf, x0f, sf, 1.0, 4.0, 20, 0)
     assert_bits(x, xf[:, ::-1], "flip")
+
+
+def test_async_transfers_match_blocking_ones(fb, oracle_mod):
+    """fruid_*_upload_async / _download_async (staged on a copy stream, overlapping the kernels) must give the
+    same fields as the blocking calls -- here checked against the oracle over three pipelined steps."""
+    w, h = 260, 150
+    L = fb._lib.lib
+    rng = np.random.default_rng(31)
+    srcs = [[rand_field(rng, w, h) for _ in range(3)] for _ in range(3)]   # per step: u_prev, v_prev, dens_prev
+    u0, v0, d0 = rand_field(rng, w, h), rand_field(rng, w, h), rand_field(rng, w, h)
+    sim, den = fb.FluidSim(w, h), fb.DensitySim(w, h)
+    fb._lib.check(L.fruid_fluid_upload(sim._h, 0, fb._lib.ptr(u0)))
+    fb._lib.check(L.fruid_fluid_upload(sim._h, 1, fb._lib.ptr(v0)))
+    fb._lib.check(L.fruid_density_upload(den._h, 0, fb._lib.ptr(d0)))
+    outs = [np.empty((h, w), np.float32) for _ in range(3)]
+    for a in [x for s3 in srcs for x in s3] + outs:
+        fb._lib.check(L.fruid_host_register(a.ctypes.data, a.nbytes))
+    of, od = oracle_mod.Fluid(w, h), oracle_mod.Density(w, h)
+    of.u[:], of.v[:], od.dens[:] = u0, v0, d0
+    want = []
+
+    def push(i):
+        fb._lib.check(L.fruid_fluid_upload_async(sim._h, 2, fb._lib.ptr(srcs[i][0])))
+        fb._lib.check(L.fruid_fluid_upload_async(sim._h, 3, fb._lib.ptr(srcs[i][1])))
+        fb._lib.check(L.fruid_density_upload_async(den._h, 1, fb._lib.ptr(srcs[i][2])))
+
+    push(0)
+    for i in range(3):
+        fb._lib.check(L.fruid_fluid_step(sim._h, 0.05, 1e-4))
+        fb._lib.check(L.fruid_density_step_dev(den._h, sim._h, 0.05, 1e-4))
+        if i + 1 < 3:
+            push(i + 1)
+        fb._lib.check(L.fruid_density_download_async(den._h, 0, fb._lib.ptr(outs[i])))
+        of.u_prev[:], of.v_prev[:], od.dens_prev[:] = srcs[i]
+        of.step(0.05, 1e-4)
+        od.step((of.u, of.v), 0.05, 1e-4)
+        want.append(od.dens.copy())
+    fb._lib.check(L.fruid_fluid_sync(sim._h))
+    fb._lib.check(L.fruid_density_sync(den._h))
+    for i in range(3):
+        assert_bits(outs[i], want[i], f"dens after step {i}")
+    for a in [x for s3 in srcs for x in s3] + outs:
+        L.fruid_host_unregister(a.ctypes.data)
