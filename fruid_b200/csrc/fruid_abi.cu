@@ -23,6 +23,7 @@
 #include "kernels_vec.cuh"
 #include "jacobi_tile.cuh"
 #include "slab_comm.cuh"
+#include "draw.cuh"
 
 using namespace fruid;
 
@@ -990,6 +991,46 @@ extern "C" int fruid_density_step_host(fruid_density_t* d, const float* u, const
 }
 extern "C" void* fruid_density_stream(fruid_density_t* d) { return d ? (void*)d->s.stream : nullptr; }
 extern "C" int fruid_density_sync(fruid_density_t* d) { NEED(d); CU(cudaStreamSynchronize(d->s.stream)); TRY(d->s.sync_copies()); CU(cudaGetLastError()); return d->s.check_peer_error(); }
+
+// draw_density (src/main.rs:146-183) on the device: vertices (24 floats per cell, reference push order)
+// or compact RGB (3 floats per cell, x + y*w order) of the four dye simulations, copied to the host.
+static int draw_density_impl(fruid_density_t* c, fruid_density_t* m, fruid_density_t* y, fruid_density_t* k, float z,
+                             float* host, bool verts) {
+    if (!c || !m || !y || !k || !host) return fail(FRUID_ERR_BAD_ARG, "null handle or host pointer");
+    FieldSet& S = c->s;
+    CU(cudaSetDevice(S.device));
+    fruid_density_t* all[4] = {c, m, y, k};
+    for (fruid_density_t* d : all) {
+        if (d->s.g.w != S.g.w || d->s.g.gh != S.g.gh) return fail(FRUID_ERR_SIZE_MISMATCH, "dye fields differ in size");
+        if (d->s.is_slab() || d->s.device != S.device) return fail(FRUID_ERR_BAD_ARG, "draw_density needs whole single-GPU fields on one device");
+    }
+    for (int i = 1; i < 4; ++i) {  // the other dyes' steps must have finished before we read them
+        CU(cudaEventRecord(all[i]->s.ev, all[i]->s.stream));
+        CU(cudaStreamWaitEvent(S.stream, all[i]->s.ev, 0));
+    }
+    const size_t per_cell = verts ? 24 : 3;
+    const size_t bytes = (size_t)S.g.w * S.g.h * per_cell * sizeof(float);
+    float* dev = nullptr;
+    CU(cudaMallocAsync(&dev, bytes, S.stream));
+    const dim3 grid((S.g.w + 31) / 32, (S.g.h + 31) / 32), block(32, 8);
+    const float cw = 2.0f / (float)S.g.w, ch = 2.0f / (float)S.g.h;  // main.rs:147-148
+    if (verts)
+        LAUNCH("k_draw_density", S.stream, (k_draw_density<true><<<grid, block, 0, S.stream>>>(c->s.buf[0], m->s.buf[0], y->s.buf[0], k->s.buf[0], S.g, z, cw, ch, dev)));
+    else
+        LAUNCH("k_draw_density_rgb", S.stream, (k_draw_density<false><<<grid, block, 0, S.stream>>>(c->s.buf[0], m->s.buf[0], y->s.buf[0], k->s.buf[0], S.g, z, cw, ch, dev)));
+    CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, S.stream));
+    CU(cudaFreeAsync(dev, S.stream));
+    CU(cudaStreamSynchronize(S.stream));
+    return 0;
+}
+extern "C" int fruid_draw_density(fruid_density_t* c, fruid_density_t* m, fruid_density_t* y, fruid_density_t* k, float z,
+                                  float* host_vertices) {
+    return draw_density_impl(c, m, y, k, z, host_vertices, true);
+}
+extern "C" int fruid_density_colors(fruid_density_t* c, fruid_density_t* m, fruid_density_t* y, fruid_density_t* k,
+                                    float* host_rgb) {
+    return draw_density_impl(c, m, y, k, 0.0f, host_rgb, false);
+}
 
 // Page-lock caller-owned host arrays (the Vec<f32> inside an Array2D has a fixed length for
 // the object's life) so uploads/downloads run at full PCIe rate.

@@ -255,22 +255,34 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
     const bool vall = v0 && v1 && v2 && v3;
     if (!EDGE) {
         // Interior tile: [xlo, xhi) = [ox+H, ox+128-H) with H even, so a lane stores its whole
-        // float4, its low or high half (8-byte aligned), or nothing -- no per-component tests.
+        // float4, its low or high half (8-byte aligned), or nothing.  One branch on the lane's
+        // mode outside the row loop; inside it only a predicated store per row.
         const int lo = A.H - 4 * lane, hi = 128 - A.H - 4 * lane;  // my components [lo, hi) are stored
         const int mode = (lo <= 0 && hi >= 4) ? 1 : (lo <= 0 && hi == 2) ? 2 : (lo == 2 && hi >= 4) ? 3 : 0;
+        const unsigned rlo = (unsigned)max(0, ylo - gyw), rcnt = (unsigned)max(0, min(R, yhi - gyw) - (int)rlo);
+        float* const o0 = A.out + (size_t)gyw * g.pitch + gx0;
+        float* const z0 = (A.fuse_src && A.z_out) ? A.z_out + (size_t)gyw * g.pitch + gx0 : nullptr;
+        const size_t pitch = g.pitch;
+        if (mode == 1) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int gy = gyw + r;
-            if (gy < ylo || gy >= yhi) continue;  // warp-uniform
-            float* row = A.out + (size_t)gy * g.pitch + gx0;
-            if (mode == 1) *reinterpret_cast<float4*>(row) = xr[r];
-            else if (mode == 2) *reinterpret_cast<float2*>(row) = make_float2(xr[r].x, xr[r].y);
-            else if (mode == 3) *reinterpret_cast<float2*>(row + 2) = make_float2(xr[r].z, xr[r].w);
-            if (A.fuse_src && A.z_out) {
-                float* zr = A.z_out + (size_t)gy * g.pitch + gx0;
-                if (mode == 1) *reinterpret_cast<float4*>(zr) = z[r];
-                else if (mode == 2) *reinterpret_cast<float2*>(zr) = make_float2(z[r].x, z[r].y);
-                else if (mode == 3) *reinterpret_cast<float2*>(zr + 2) = make_float2(z[r].z, z[r].w);
+            for (int r = 0; r < R; ++r)
+                if ((unsigned)r - rlo < rcnt) *reinterpret_cast<float4*>(o0 + r * pitch) = xr[r];
+            if (z0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if ((unsigned)r - rlo < rcnt) *reinterpret_cast<float4*>(z0 + r * pitch) = z[r];
+            }
+        } else if (mode != 0) {
+            const int sh = (mode == 3) ? 2 : 0;  // which half of the float4
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if ((unsigned)r - rlo < rcnt)
+                    *reinterpret_cast<float2*>(o0 + r * pitch + sh) = sh ? make_float2(xr[r].z, xr[r].w) : make_float2(xr[r].x, xr[r].y);
+            if (z0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if ((unsigned)r - rlo < rcnt)
+                        *reinterpret_cast<float2*>(z0 + r * pitch + sh) = sh ? make_float2(z[r].z, z[r].w) : make_float2(z[r].x, z[r].y);
             }
         }
         return;

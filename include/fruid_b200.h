@@ -134,6 +134,16 @@ int fruid_density_step_host(fruid_density_t *d, const float *u, const float *v, 
 int fruid_density_sync(fruid_density_t *d);
 void *fruid_density_stream(fruid_density_t *d);
 
+/* ---- Next to the solver: draw_density of the reference viewer, src/main.rs:146-183 ----
+ * Computes on the device, from the density() fields of the four dye simulations (c, m, y, k), what
+ * the viewer rebuilds on the CPU every frame: the vertex buffer {pos[3], color[3]} x 4 per cell in the
+ * reference's push order (i outer, j inner; tl, tr, bl, br) -- host_vertices holds w*h*24 floats -- or
+ * just the RGB colour of every cell (host_rgb: w*h*3 floats, cell (x, y) at 3*(x + y*w)). */
+int fruid_draw_density(fruid_density_t *c, fruid_density_t *m, fruid_density_t *y, fruid_density_t *k, float z,
+                       float *host_vertices);
+int fruid_density_colors(fruid_density_t *c, fruid_density_t *m, fruid_density_t *y, fruid_density_t *k,
+                         float *host_rgb);
+
 /* ---- Multi-GPU y-slabs: one process per GPU -----------------------------------
  * Rank `rank` of `world` (<= 8) owns global rows [y0, y1) of the w x gh field plus 22 halo rows
  * of each neighbour.  After creation every rank exports a 64-byte CUDA IPC handle of its device

@@ -237,3 +237,41 @@ int fruid_oracle_has_openmp(void) {
     return 0;
 #endif
 }
+
+/* ---- "next" row f-2: draw_density, src/main.rs:146-183 -------------------------
+ * Per cell (i outer, j inner): CMY dye -> RGB colour log2((1 - f - k)/max(|cmy|, 1) + 2) and four
+ * vertices {pos[3], color[3]} (tl, tr, bl, br).  `verts` holds w*h*4*6 floats in push order.
+ * log2 is libm's log2f here and CUDA's log2f on the device: colours agree to a couple of ulps,
+ * positions bit for bit. */
+#include <math.h>
+void fruid_oracle_draw_density(const float *c, const float *m, const float *y, const float *k, size_t w,
+                               size_t h, float z, float *verts) {
+    float cell_width = 2.0f / (float)w;
+    float cell_height = 2.0f / (float)h;
+    size_t n = 0;
+    for (size_t i = 0; i < w; ++i) {
+        float i_frac = ((float)i / (float)w) * 2.0f - 1.0f;
+        for (size_t j = 0; j < h; ++j) {
+            float j_frac = ((float)j / (float)h) * 2.0f - 1.0f;
+            float kk = k[IDX(i, j, w)];
+            float cmy[3] = {c[IDX(i, j, w)], m[IDX(i, j, w)], y[IDX(i, j, w)]};
+            float sum = 0.0f;
+            for (int d = 0; d < 3; ++d) sum = sum + cmy[d] * cmy[d];
+            float total = sqrtf(sum);
+            float denom = (total > 1.0f || total != total) ? total : 1.0f; /* f32::max(total, 1.) */
+            if (total != total) denom = 1.0f;                              /* NaN.max(1.) == 1. */
+            float col[3];
+            for (int d = 0; d < 3; ++d) col[d] = log2f((1.0f - cmy[d] - kk) / denom + 2.0f);
+            float dx[4] = {0.0f, cell_width, 0.0f, cell_width};
+            float dy[4] = {0.0f, 0.0f, cell_height, cell_height};
+            for (int q = 0; q < 4; ++q) {
+                verts[n++] = i_frac + dx[q];
+                verts[n++] = j_frac + dy[q];
+                verts[n++] = z;
+                verts[n++] = col[0];
+                verts[n++] = col[1];
+                verts[n++] = col[2];
+            }
+        }
+    }
+}

@@ -199,3 +199,26 @@ def test_golden_scene_checksums_128(oracle_mod):
     s.run(100)
     for k, a in _scene_fields(s).items():
         assert hashlib.sha256(a.tobytes()).hexdigest() == sums["sha256"][k], k
+
+
+def test_draw_density_known_answers(oracle_mod):
+    """main.rs:146-183: with no dye every colour channel is log2((1 - 0 - 0)/max(0, 1) + 2) = log2(3); cell
+    (i, j) is the (i*h + j)-th quad, its corners at i_frac, i_frac + 2/w; z is passed through."""
+    w, h = 6, 4
+    z = np.zeros((h, w), np.float32)
+    v = np.zeros(w * h * 24, np.float32)
+    oracle_mod.lib().fruid_oracle_draw_density(z, z, z, z, w, h, 0.25, v)
+    v = v.reshape(w, h, 4, 6)
+    assert np.allclose(v[..., 3:], np.log2(3.0), rtol=1e-6)
+    assert np.all(v[..., 2] == 0.25)
+    i, j = 2, 3
+    x0 = np.float32(np.float32(i) / np.float32(w)) * np.float32(2) - np.float32(1)
+    y0 = np.float32(np.float32(j) / np.float32(h)) * np.float32(2) - np.float32(1)
+    assert v[i, j, 0, 0] == x0 and v[i, j, 0, 1] == y0                     # tl
+    assert v[i, j, 1, 0] == x0 + np.float32(2.0 / w) and v[i, j, 1, 1] == y0  # tr
+    assert v[i, j, 2, 0] == x0 and v[i, j, 2, 1] == y0 + np.float32(2.0 / h)  # bl
+    # heavy dye: colours divide by |cmy|
+    c = np.full((h, w), 3.0, np.float32)
+    oracle_mod.lib().fruid_oracle_draw_density(c, z, z, z, w, h, 0.0, v.reshape(-1))
+    assert np.allclose(v[..., 3], np.log2((1 - 3.0) / 3.0 + 2), rtol=1e-6)
+    assert np.allclose(v[..., 4], np.log2(1 / 3.0 + 2), rtol=1e-6)

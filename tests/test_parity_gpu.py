@@ -479,3 +479,40 @@ def test_async_transfers_match_blocking_ones(fb, oracle_mod):
         assert_bits(outs[i], want[i], f"dens after step {i}")
     for a in [x for s3 in srcs for x in s3] + outs:
         L.fruid_host_unregister(a.ctypes.data)
+
+
+# ---- next row: device-side draw_density + frame dump --------------------------
+def _ulp_diff(a, b):
+    ai = a.view(np.int32).astype(np.int64)
+    bi = b.view(np.int32).astype(np.int64)
+    ai = np.where(ai < 0, -(ai & 0x7fffffff), ai)
+    bi = np.where(bi < 0, -(bi & 0x7fffffff), bi)
+    return np.abs(ai - bi)
+
+
+@pytest.mark.parametrize("w,h", [(250, 250), (33, 70), (128, 128)])
+def test_draw_density_matches_reference_viewer(fb, oracle_mod, w, h, tmp_path):
+    """draw_density (main.rs:146-183): vertex positions bit-exact, colours within 4 ulp or 2e-7 absolute
+    of the CPU restatement (log2f: CUDA's vs glibc's, both <= 1 ulp from the true value; near log2(1) = 0 the
+    result is tiny, hence the absolute term)."""
+    rng = np.random.default_rng(w + h)
+    dyes, fields = [], []
+    for scale in (3.0, 0.5, 2.0, 0.1):
+        d = fb.DensitySim(w, h)
+        a = (rng.random((h, w)) * scale).astype(np.float32)
+        fb._lib.check(fb._lib.lib.fruid_density_upload(d._h, 0, fb._lib.ptr(a)))
+        dyes.append(d)
+        fields.append(a)
+    got = fb.render.draw_density(*dyes, z=0.5)
+    want = np.zeros(w * h * 24, np.float32)
+    oracle_mod.lib().fruid_oracle_draw_density(*fields, w, h, 0.5, want)
+    want = want.reshape(-1, 6)
+    assert_bits(got[:, :3], want[:, :3], "positions")
+    ulps = _ulp_diff(np.ascontiguousarray(got[:, 3:]), np.ascontiguousarray(want[:, 3:]))
+    close = (ulps <= 4) | (np.abs(got[:, 3:] - want[:, 3:]) <= 2e-7)
+    assert close.all(), f"max ulp {ulps.max()}"
+    rgb = fb.render.density_colors(*dyes)
+    # same colours, x + y*w order instead of the push order
+    assert np.array_equal(rgb, got[::4, 3:].reshape(w, h, 3).transpose(1, 0, 2))
+    fb.render.write_ppm(str(tmp_path / "frame.ppm"), rgb)
+    assert (tmp_path / "frame.ppm").stat().st_size == len(b"P6\n%d %d\n255\n" % (w, h)) + w * h * 3
