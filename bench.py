@@ -450,6 +450,10 @@ def run_b200_multi(args, fb, dist, rank, world, local):
     _lib.profile_enable(False)
     dist.barrier()
     kernels_ms = {k: [n // 3, round(t / 3, 4)] for k, (n, t) in sorted(stats.items())}
+    compute_ms = round(sum(t for k, (n, t) in stats.items() if not k.startswith("k_slab")) / 3, 4)
+    comm_ms = round(sum(t for k, (n, t) in stats.items() if k.startswith("k_slab")) / 3, 4)
+    per_rank_split = [None] * world
+    dist.all_gather_object(per_rank_split, (compute_ms, comm_ms))
 
     # end to end: every step each rank uploads its rows of the three source fields and downloads
     # its rows of the density (host <-> device inside the timed region), wall clock, max over ranks
@@ -495,7 +499,8 @@ def run_b200_multi(args, fb, dist, rank, world, local):
                              "traffic": None, "note": "per-GPU algorithmic bytes (188+60K per cell-step) / time; see the "
                                                       "N=1 line for the dominant kernel"},
                 "cpu_baseline": None, "impl": "b200", "kernels_launches_ms_per_step_rank0": kernels_ms,
-                "per_rank_ms_per_step_gpu_and_host_enqueue": per_rank}
+                "per_rank_ms_per_step_gpu_and_host_enqueue": per_rank,
+                "per_rank_ms_per_step_compute_and_comm_kernels": per_rank_split}
         print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()

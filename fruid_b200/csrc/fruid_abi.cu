@@ -621,7 +621,9 @@ struct FieldSet {
             ++slot;
         }
         A.njobs = nj;
-        LAUNCH("k_slab_pull", stream, (k_slab_pull<<<dim3(32, nj), 256, 0, stream>>>(A)));
+        // enough CTAs to keep ~2-3 MB in flight over NVLink for wide grids, one pass for narrow ones
+        const int ctas = (int)std::min<size_t>(64, std::max<size_t>(8, (g.pitch * SLAB_HALO / 4 + 1023) / 1024));
+        LAUNCH("k_slab_pull", stream, (k_slab_pull<<<dim3(ctas, nj), 256, 0, stream>>>(A)));
         return 0;
     }
     int barrier() {
@@ -733,7 +735,10 @@ static int op_vel_step_slab(FieldSet& S, float visc, float dt) {
     return project_slab(S, u, v, u0, v0, T);                                           // lib.rs:207
 }
 
-static int op_dens_step_slab(FieldSet& S, const float* u, const float* v, float diff, float dt) {
+// `vel_ready` (recorded on the velocity handle's stream after its step) is awaited only right before
+// the advect: the halo exchange and the diffusion solve do not read the velocity, so they (and the
+// waiting inside the exchange) overlap the tail of the velocity step running on the other stream.
+static int op_dens_step_slab(FieldSet& S, const float* u, const float* v, float diff, float dt, cudaEvent_t vel_ready) {
     TRY(S.need_peers());
     const Geom& g = S.g;
     cudaStream_t st = S.stream;
@@ -747,6 +752,7 @@ static int op_dens_step_slab(FieldSet& S, const float* u, const float* v, float 
     TRY(op_lin_solve(B_POSITIVE, x0, x, s, g, a, c, S.iters, T, st, false, true, dt, s2, &sd));  // lib.rs:172,175
     S.slab.ev_adv += 1;
     TRY(S.signal_all(0));                      // my x0 is final
+    CU(cudaStreamWaitEvent(st, vel_ready, 0)); // u, v of this step
     SlabTable tab{};
     TRY(S.fill_table(tab, 0, x0));
     float* d[1] = {x};
@@ -955,13 +961,13 @@ extern "C" int fruid_density_step_dev(fruid_density_t* d, fruid_fluid_t* vel, fl
         return fail(FRUID_ERR_SIZE_MISMATCH, "density %dx%d vs velocity %dx%d", s.g.w, s.g.gh, vs.g.w, vs.g.gh);
     if (vs.device != s.device) return fail(FRUID_ERR_BAD_ARG, "density and velocity live on different devices");
     TRY(s.consume_uploads());
-    // u,v are produced on vel's stream and consumed on ours; order both ways.
-    CU(cudaEventRecord(vs.ev, vs.stream));
-    CU(cudaStreamWaitEvent(s.stream, vs.ev, 0));
     if (s.is_slab() != vs.is_slab() || s.slab.world != vs.slab.world || s.slab.rank != vs.slab.rank)
         return fail(FRUID_ERR_SIZE_MISMATCH, "density and velocity handles are decomposed differently");
+    // u,v are produced on vel's stream and consumed on ours; order both ways.
+    CU(cudaEventRecord(vs.ev, vs.stream));
+    if (!s.is_slab()) CU(cudaStreamWaitEvent(s.stream, vs.ev, 0));
     if (s.is_slab())
-        TRY(op_dens_step_slab(s, vs.buf[0], vs.buf[1], diff, dt));
+        TRY(op_dens_step_slab(s, vs.buf[0], vs.buf[1], diff, dt, vs.ev));
     else
         TRY(run_step_graphed(s, dt, diff, vs.buf[0], vs.buf[1], [&]() {
             return op_dens_step(s.buf[0], s.buf[1], vs.buf[0], vs.buf[1], s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream);
