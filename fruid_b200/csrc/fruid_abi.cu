@@ -380,6 +380,14 @@ struct FieldSet {
     int fused = 0;   // 0 = library default
     int device = 0;
     SlabInfo slab;
+    // Slab mode: events of other handles' streams (density steps) that still READ my u, v; awaited
+    // lazily right before the step first overwrites u or v instead of at the step's start.
+    std::vector<cudaEvent_t> readers;
+    int wait_readers() {
+        for (cudaEvent_t e : readers) CU(cudaStreamWaitEvent(stream, e, 0));
+        readers.clear();
+        return 0;
+    }
 
     bool is_slab() const { return slab.world > 1; }
     // local rows [lo, hi) that this rank owns
@@ -452,6 +460,7 @@ struct FieldSet {
     // Host arrays cover the rows this rank OWNS (the whole field on one GPU), dense w floats per row.
     int upload(int field, const float* host) {
         if (field < 0 || field >= n_user || !host) return fail(FRUID_ERR_BAD_ARG, "bad field %d or null host pointer", field);
+        TRY(wait_readers());
         CU(cudaMemcpy2DAsync(buf[field] + (size_t)own_lo() * g.pitch, g.pitch * sizeof(float), host, (size_t)g.w * sizeof(float),
                              (size_t)g.w * sizeof(float), (size_t)(own_hi() - own_lo()), cudaMemcpyHostToDevice, stream));
         CU(cudaStreamSynchronize(stream));  // host buffer may be pageable and reused by the caller
@@ -491,6 +500,7 @@ struct FieldSet {
     int consume_uploads() {
         for (int f = 0; f < 4; ++f) {
             if (!up_pending[f]) continue;
+            TRY(wait_readers());
             CU(cudaStreamWaitEvent(stream, up_ev[f], 0));
             const size_t rows = (size_t)(own_hi() - own_lo());
             CU(cudaMemcpyAsync(buf[f] + (size_t)own_lo() * g.pitch, up_stage[f], g.pitch * rows * sizeof(float),
@@ -533,6 +543,7 @@ struct FieldSet {
         if (x >= (size_t)g.w || y >= (size_t)g.gh) return fail(FRUID_ERR_BAD_ARG, "cell (%zu,%zu) outside %dx%d", x, y, g.w, g.gh);
         const int ly = (int)y - g.gy0;
         if (ly < own_lo() || ly >= own_hi()) return 0;
+        TRY(wait_readers());
         CU(cudaMemcpyAsync(buf[field] + x + (size_t)ly * g.pitch, &val, sizeof(float), cudaMemcpyHostToDevice, stream));
         return 0;
     }
@@ -716,7 +727,8 @@ static int op_vel_step_slab(FieldSet& S, float visc, float dt) {
         TRY(op_lin_solve(B_NEGY, v0, v, s, g, a, c, S.iters, T, st, false, true, dt, s2, &sv));
     }
     TRY(S.exchange({u0, v0}));
-    TRY(project_slab(S, u0, v0, u, v, T));                                             // lib.rs:199
+    TRY(S.wait_readers());                     // density steps of the previous scene step have read u, v
+    TRY(project_slab(S, u0, v0, u, v, T));                                             // lib.rs:199 (overwrites u, v)
     S.slab.ev_adv += 1;
     TRY(S.signal_all(0));                      // my u0, v0 are final: owners' rows may be gathered
     {
@@ -973,7 +985,11 @@ extern "C" int fruid_density_step_dev(fruid_density_t* d, fruid_fluid_t* vel, fl
             return op_dens_step(s.buf[0], s.buf[1], vs.buf[0], vs.buf[1], s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream);
         }));
     CU(cudaEventRecord(s.ev, s.stream));
-    CU(cudaStreamWaitEvent(vs.stream, s.ev, 0));
+    if (s.is_slab()) {
+        if (std::find(vs.readers.begin(), vs.readers.end(), s.ev) == vs.readers.end()) vs.readers.push_back(s.ev);
+    } else {
+        CU(cudaStreamWaitEvent(vs.stream, s.ev, 0));
+    }
     return 0;
 }
 extern "C" int fruid_density_step_host(fruid_density_t* d, const float* u, const float* v, float dt, float diff) {
