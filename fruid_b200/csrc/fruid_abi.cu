@@ -345,7 +345,6 @@ struct StepGraph {
     const void* a0 = nullptr;      // density: the velocity pointers the graph was captured with
     const void* a1 = nullptr;
     uint64_t kernels = 0;          // kernel launches inside the graph
-    int direct_steps = 0;          // steps run without a graph (the first one warms allocations and caches)
     bool failed = false;           // capture did not work for these parameters: stay on direct launches
     bool matches(float dt_, float p_, int it, int fu, const void* b0, const void* b1) const {
         return dt == dt_ && p == p_ && iters == it && fused == fu && a0 == b0 && a1 == b1;
@@ -783,18 +782,21 @@ template <class Body>
 static int run_step_graphed(FieldSet& S, float dt, float p, const void* a0, const void* a1, Body body) {
     StepGraph& G = S.graph;
     const bool usable = g_graphs_enabled && !g_prof_on && !S.is_slab();
-    if (usable && G.exec && G.matches(dt, p, S.iters, S.fused, a0, a1)) {
+    if (!usable) return body();
+    if (!G.matches(dt, p, S.iters, S.fused, a0, a1)) {
+        // first step with these parameters: run it directly (it warms lazy allocations, tensor maps and
+        // the divisor check, none of which may happen inside a capture) and remember the parameters
+        G.reset();
+        G.dt = dt; G.p = p; G.iters = S.iters; G.fused = S.fused; G.a0 = a0; G.a1 = a1;
+        return body();
+    }
+    if (G.exec) {
         CU(cudaGraphLaunch(G.exec, S.stream));
         g_launches.fetch_add(G.kernels, std::memory_order_relaxed);
         return 0;
     }
-    if (!usable || G.direct_steps < 1 || (G.failed && G.matches(dt, p, S.iters, S.fused, a0, a1))) {
-        G.direct_steps += 1;
-        return body();
-    }
-    // capture
-    G.reset();
-    G.dt = dt; G.p = p; G.iters = S.iters; G.fused = S.fused; G.a0 = a0; G.a1 = a1;
+    if (G.failed) return body();
+    // second step with the same parameters: capture it
     float* before[6];
     for (int i = 0; i < 6; ++i) before[i] = S.buf[i];
     const uint64_t k0 = g_launches.load();

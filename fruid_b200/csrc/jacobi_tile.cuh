@@ -31,9 +31,17 @@
 // with 1/c when c is a power of two (bit-identical: same real value, same rounding);
 // MODE_ONE drops it when c == 1; MODE_POISSON additionally drops the multiplication by
 // a == 1 (1*sum == sum bit-for-bit).  Otherwise a*sum is always computed (0*inf etc.).
+// MODE_RECIP divides by a general c without the ~25-instruction IEEE division sequence: with the
+// reciprocal as a double-word (zh, zl), q = fma(v, zh, v*zl) is the correctly rounded v/c (division
+// by a constant with an FMA, Brisebarre-Muller-Raina 2004) -- for "almost all" c; the claim is not
+// taken on trust: before a value of c is used, a kernel compares q with __fdiv_rn(v, c) for ALL 2^23
+// significands of v (results scale exactly with the exponent while nothing under/overflows), and
+// falls back to MODE_GENERAL if a single one differs.  Inputs outside [2^-60, 2^60) (zeros,
+// denormals, huge values, inf, NaN) take __fdiv_rn per element.
 #pragma once
 #include <cuda.h>
 
+#include <cstring>
 #include <iterator>
 #include <mutex>
 #include <unordered_map>
@@ -42,7 +50,7 @@
 
 namespace fruid {
 
-enum : int { MODE_GENERAL = 0, MODE_POW2 = 1, MODE_ONE = 2, MODE_POISSON = 3 };
+enum : int { MODE_GENERAL = 0, MODE_POW2 = 1, MODE_ONE = 2, MODE_POISSON = 3, MODE_RECIP = 4 };
 
 struct TileArgs {
     CUtensorMap tm_x0;  // 2-D map over x0: dims (pitch, h) f32, box (128, R*NW), zero OOB fill
@@ -51,6 +59,7 @@ struct TileArgs {
     const float* x;
     Geom g;
     float a, c;  // c holds 1/c in MODE_POW2 / MODE_POISSON
+    float zh, zl;  // MODE_RECIP: 1/c as a double-word (zh = RN(1/c), zl = RN(1/c - zh))
     int b;       // bounds kind
     int T;       // sweeps in this launch
     int H;       // halo = T rounded up to even
@@ -89,9 +98,12 @@ __device__ __forceinline__ void tile_of_item(int item, int ntx, int nty, int& kx
 // bit-identical to two scalar ones), which halves the issue pressure of this issue-bound
 // kernel.  Order of operations is exactly lib.rs:61-65: ((l + r) + u) + d, then
 // (x0 + a*sum) / c.
+__device__ __forceinline__ bool recip_safe(float v) {  // 2^-60 <= |v| < 2^60
+    return ((__float_as_uint(v) & 0x7f800000u) - (67u << 23)) < (120u << 23);
+}
 template <int MODE>
 __device__ __forceinline__ float4 jac_row(const float4 z, float t0, float t1, float t2, float t3, const float4 up,
-                                          const float4 dn, float a, float c) {
+                                          const float4 dn, float a, float c, float zh = 0.f, float zl = 0.f) {
     float2 s01 = __fadd2_rn(make_float2(t0, t1), make_float2(up.x, up.y));
     float2 s23 = __fadd2_rn(make_float2(t2, t3), make_float2(up.z, up.w));
     s01 = __fadd2_rn(s01, make_float2(dn.x, dn.y));
@@ -106,6 +118,15 @@ __device__ __forceinline__ float4 jac_row(const float4 z, float t0, float t1, fl
     s01 = __fadd2_rn(make_float2(z.x, z.y), s01);
     s23 = __fadd2_rn(make_float2(z.z, z.w), s23);
     if (MODE == MODE_GENERAL) return make_float4(fdiv(s01.x, c), fdiv(s01.y, c), fdiv(s23.x, c), fdiv(s23.y, c));
+    if (MODE == MODE_RECIP) {
+        // an FMA used as an exact-arithmetic building block of the division, not a contraction
+        const float2 q01 = __ffma2_rn(s01, make_float2(zh, zh), __fmul2_rn(s01, make_float2(zl, zl)));
+        const float2 q23 = __ffma2_rn(s23, make_float2(zh, zh), __fmul2_rn(s23, make_float2(zl, zl)));
+        const bool k0 = recip_safe(s01.x), k1 = recip_safe(s01.y), k2 = recip_safe(s23.x), k3 = recip_safe(s23.y);
+        if (k0 & k1 & k2 & k3) return make_float4(q01.x, q01.y, q23.x, q23.y);
+        return make_float4(k0 ? q01.x : fdiv(s01.x, c), k1 ? q01.y : fdiv(s01.y, c), k2 ? q23.x : fdiv(s23.x, c),
+                           k3 ? q23.y : fdiv(s23.y, c));
+    }
     if (MODE == MODE_POW2 || MODE == MODE_POISSON) {
         s01 = __fmul2_rn(s01, make_float2(c, c));
         s23 = __fmul2_rn(s23, make_float2(c, c));
@@ -147,7 +168,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
 
 // EDGE tiles: flags saying which of my components sit next to a domain border column
 // (gx == 1: left neighbour is border column 0; gx == w-2: right neighbour is column w-1).
-struct EdgeFlags { bool l1, r0, r1, r2, r3, negx, negy; int h; };
+struct EdgeFlags { bool l1, r0, r1, r2, r3, negx, negy; int h; float zh, zl; };
 
 // New value of one float4 row from its old value cc, the rows above/below and x0 (z).
 template <int MODE, bool EDGE>
@@ -167,7 +188,7 @@ __device__ __forceinline__ float4 jac_row_full(float4 cc, float4 up, float4 dn, 
         if (sub && E.r3) rgt = sgn(E.negx, cc.w);
     }
     const float t0 = fadd(lft, rx), t1 = fadd(ly, ry), t2 = fadd(cc.y, rz), t3 = fadd(cc.z, rgt);  // l + r
-    return jac_row<MODE>(z, t0, t1, t2, t3, up, dn, a, c);
+    return jac_row<MODE>(z, t0, t1, t2, t3, up, dn, a, c, E.zh, E.zl);
 }
 
 template <int R, int NW, int MODE, bool EDGE>
@@ -188,6 +209,7 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
     EdgeFlags E;
     E.l1 = E.r0 = E.r1 = E.r2 = E.r3 = false;
     E.negx = negx; E.negy = negy; E.h = g.gh;
+    E.zh = A.zh; E.zl = A.zl;
     if (EDGE) {
         E.l1 = (gx0 + 1 == 1);  // ox == 0 && lane == 0 (tile origins are multiples of 4)
         E.r0 = (gx0 + 0 == g.w - 2); E.r1 = (gx0 + 1 == g.w - 2); E.r2 = (gx0 + 2 == g.w - 2); E.r3 = (gx0 + 3 == g.w - 2);
@@ -439,7 +461,55 @@ __global__ void __launch_bounds__(NW * 32, 1) k_jacobi_tile(const __grid_constan
     }
 }
 
+// Exhaustive check of the MODE_RECIP division for one divisor: all 2^23 significands, two binades, both signs.
+__global__ void k_recip_verify(float c, float zh, float zl, int* bad) {
+    const unsigned m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= (1u << 23)) return;
+    int b = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const unsigned bits = ((k & 1) ? 0x42000000u : 0x3f800000u) | ((k & 2) ? 0x80000000u : 0u) | m;
+        const float v = __uint_as_float(bits);
+        const float q = __fmaf_rn(v, zh, __fmul_rn(v, zl));
+        b |= (__float_as_uint(q) != __float_as_uint(__fdiv_rn(v, c)));
+    }
+    if (b) atomicOr(bad, 1);
+}
+
 // ---- host side -----------------------------------------------------------------------------
+// c -> (usable, zh, zl); filled by recip_for() the first time a divisor is seen (synchronises once).
+struct RecipInfo { bool ok; float zh, zl; };
+static std::mutex g_recip_mu;
+static std::unordered_map<uint32_t, RecipInfo> g_recip;
+static bool recip_for(float c, RecipInfo* out) {
+    uint32_t key;
+    memcpy(&key, &c, 4);
+    std::lock_guard<std::mutex> lk(g_recip_mu);
+    auto it = g_recip.find(key);
+    if (it != g_recip.end()) { *out = it->second; return it->second.ok; }
+    RecipInfo r{false, 0.f, 0.f};
+    int e = 0;
+    (void)frexpf(c, &e);
+    if (c == c && c != 0.f && e > -30 && e < 30) {  // finite, normal, moderate magnitude
+        r.zh = 1.0f / c;
+        r.zl = (float)(1.0 / (double)c - (double)r.zh);
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        int* bad = nullptr;
+        // never synchronise inside a stream capture: leave the divisor unverified (general path) for now
+        if (cudaStreamIsCapturing(cudaStreamPerThread, &cs) == cudaSuccess && cudaMalloc(&bad, sizeof(int)) == cudaSuccess) {
+            int h = 1;
+            if (cudaMemset(bad, 0, sizeof(int)) == cudaSuccess) {
+                k_recip_verify<<<(1u << 23) / 256, 256>>>(c, r.zh, r.zl, bad);
+                if (cudaMemcpy(&h, bad, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) r.ok = (h == 0);
+            }
+            cudaFree(bad);
+        }
+    }
+    g_recip.emplace(key, r);
+    *out = r;
+    return r.ok;
+}
+
 struct TileCfg { int R, NW; };
 static TileCfg g_tile_cfg = {8, 16};
 static int g_tile_default_T = 10;
@@ -562,6 +632,7 @@ static int jacobi_tile_launch_cfg(const TileArgs& A, int mode, cudaStream_t st) 
     if (mode == MODE_GENERAL) return jacobi_tile_launch_mode<R, NW, MODE_GENERAL>(A, st);
     if (mode == MODE_POW2) return jacobi_tile_launch_mode<R, NW, MODE_POW2>(A, st);
     if (mode == MODE_POISSON) return jacobi_tile_launch_mode<R, NW, MODE_POISSON>(A, st);
+    if (mode == MODE_RECIP) return jacobi_tile_launch_mode<R, NW, MODE_RECIP>(A, st);
     return jacobi_tile_launch_mode<R, NW, MODE_ONE>(A, st);
 }
 
@@ -576,6 +647,7 @@ static int jacobi_tile_launch(float* out, const float* x, const float* x0, const
     if (int r = tile_tensor_map(x0, g.pitch, g.h, TH, &A.tm_x0)) return r;
     if (int r = tile_tensor_map(x, g.pitch, g.h, TH, &A.tm_x)) return r;
     A.out = out; A.x = x; A.g = g; A.a = a; A.b = b; A.T = T; A.x_is_zero = x_is_zero;
+    A.zh = A.zl = 0.f;
     A.fuse_src = fuse_src; A.src_dt = src_dt; A.z_out = z_out;
     A.sched = tile_sched_for(st);
     if (!A.sched) return -4;
@@ -594,6 +666,17 @@ static int jacobi_tile_launch(float* out, const float* x, const float* x0, const
         if (m == 0.5f && e > -100 && e < 100) {  // c = 2^k: multiply by the exact reciprocal
             mode = (a == 1.0f) ? MODE_POISSON : MODE_POW2;
             A.c = 1.0f / c;
+        } else {
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            RecipInfo ri;
+            const bool capturing = cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone;
+            bool known;
+            {
+                uint32_t key; memcpy(&key, &c, 4);
+                std::lock_guard<std::mutex> lk(g_recip_mu);
+                known = g_recip.count(key) != 0;
+            }
+            if ((known || !capturing) && recip_for(c, &ri)) { mode = MODE_RECIP; A.zh = ri.zh; A.zl = ri.zl; }
         }
     }
 #define FRUID_TILE_CASE(r, nw) if (R == r && NW == nw) return jacobi_tile_launch_cfg<r, nw>(A, mode, st);

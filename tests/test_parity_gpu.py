@@ -516,3 +516,23 @@ def test_draw_density_matches_reference_viewer(fb, oracle_mod, w, h, tmp_path):
     assert np.array_equal(rgb, got[::4, 3:].reshape(w, h, 3).transpose(1, 0, 2))
     fb.render.write_ppm(str(tmp_path / "frame.ppm"), rgb)
     assert (tmp_path / "frame.ppm").stat().st_size == len(b"P6\n%d %d\n255\n" % (w, h)) + w * h * 3
+
+
+@pytest.mark.parametrize("c", [1.6704, 3.924, 1.0000001, 7.3e-3, 513.77, 1.9999999])
+def test_lin_solve_general_divisor_extreme_values(fb, O, c):
+    """General c takes the verified reciprocal division (MODE_RECIP) with a per-element IEEE fallback outside
+    [2^-60, 2^60): feed zeros, -0, denormals, huge values, inf and NaN next to ordinary data."""
+    w, h = 200, 140
+    rng = np.random.default_rng(17)
+    x, x0, s = rand_field(rng, w, h), rand_field(rng, w, h), np.zeros((h, w), np.float32)
+    specials = np.array([0.0, -0.0, 1e-42, -3e-39, 1e-30, -1e-25, 1e25, -3e30, 3e38, np.inf, -np.inf, np.nan, 1e-20, 1e19],
+                        np.float32)
+    ys, xs = rng.integers(1, h - 1, 400), rng.integers(1, w - 1, 400)
+    x0[ys, xs] = rng.choice(specials, 400)
+    ys, xs = rng.integers(1, h - 1, 100), rng.integers(1, w - 1, 100)
+    x[ys, xs] = rng.choice(specials, 100)
+    xo, so = x.copy(), s.copy()
+    with np.errstate(all="ignore"):
+        fb.ops.lin_solve(NEGX, x, x0, s, 0.31, c, 20, 0)
+        O.fruid_oracle_lin_solve(NEGX, xo, x0, so, w, h, 0.31, c, 20, 1)
+    assert_bits(x, xo, "x")
