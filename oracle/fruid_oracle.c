@@ -12,8 +12,9 @@
  * image (no rustc/cargo, un-vendored dependencies, no network).  The oracle is
  * therefore pinned only by (1) a line-by-line audit against src/lib.rs (every
  * function below cites the lines it restates), (2) analytic known answers
- * derived from the source text and (3) an independent numpy restatement
- * (tests/ref_numpy.py) that must agree bit-for-bit.
+ * derived from the source text and (3) two independent restatements
+ * (tests/ref_numpy.py, vectorised; tests/ref_literal.py, a statement-by-
+ * statement scalar transliteration) that must agree bit-for-bit.
  *
  * Numeric contract (what Rust does, what this file must do):
  *   - f32 everywhere; only + - * / compare negate and float->usize casts.
