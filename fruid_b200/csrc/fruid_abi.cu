@@ -338,6 +338,7 @@ struct SlabInfo {
 
 // A captured CUDA graph of one step for fixed parameters.  The 13-16 launches of a step are
 // launch-latency bound on grids up to ~1024^2; replaying a graph removes the per-launch host cost.
+static std::atomic<int> g_cfg_epoch{0};  // bumped by every global tuning knob: captured graphs become stale
 struct StepGraph {
     cudaGraphExec_t exec = nullptr;
     float dt = 0.f, p = 0.f;       // dt and visc / diff
@@ -345,9 +346,10 @@ struct StepGraph {
     const void* a0 = nullptr;      // density: the velocity pointers the graph was captured with
     const void* a1 = nullptr;
     uint64_t kernels = 0;          // kernel launches inside the graph
+    int cfg_epoch = -1;            // value of g_cfg_epoch the parameters were recorded under
     bool failed = false;           // capture did not work for these parameters: stay on direct launches
     bool matches(float dt_, float p_, int it, int fu, const void* b0, const void* b1) const {
-        return dt == dt_ && p == p_ && iters == it && fused == fu && a0 == b0 && a1 == b1;
+        return dt == dt_ && p == p_ && iters == it && fused == fu && a0 == b0 && a1 == b1 && cfg_epoch == g_cfg_epoch.load();
     }
     void reset() {
         if (exec) cudaGraphExecDestroy(exec);
@@ -788,6 +790,7 @@ static int run_step_graphed(FieldSet& S, float dt, float p, const void* a0, cons
         // the divisor check, none of which may happen inside a capture) and remember the parameters
         G.reset();
         G.dt = dt; G.p = p; G.iters = S.iters; G.fused = S.fused; G.a0 = a0; G.a1 = a1;
+        G.cfg_epoch = g_cfg_epoch.load();
         return body();
     }
     if (G.exec) {
@@ -828,7 +831,7 @@ static int run_step_graphed(FieldSet& S, float dt, float p, const void* a0, cons
     return 0;
 }
 // Tuning / debugging knob: replay steps as CUDA graphs (default on).
-extern "C" int fruid_set_graphs_enabled(int on) { g_graphs_enabled = on != 0; return 0; }
+extern "C" int fruid_set_graphs_enabled(int on) { g_graphs_enabled = on != 0; g_cfg_epoch.fetch_add(1); return 0; }
 
 #define NEED(h) do { if (!(h)) return fail(FRUID_ERR_BAD_ARG, "null handle"); CU(cudaSetDevice((h)->s.device)); } while (0)
 
@@ -1062,6 +1065,7 @@ extern "C" int fruid_density_colors(fruid_density_t* c, fruid_density_t* m, frui
 extern "C" int fruid_set_tile_config(int rows_per_warp, int warps, int default_fused) {
     if (jacobi_tile_set_cfg(rows_per_warp, warps, default_fused) != 0)
         return fail(FRUID_ERR_BAD_ARG, "unsupported tile config R=%d NW=%d", rows_per_warp, warps);
+    g_cfg_epoch.fetch_add(1);
     return 0;
 }
 extern "C" int fruid_host_register(void* p, size_t bytes) {
