@@ -296,6 +296,25 @@ def run_b200(args):
                 "step_effective_gbs": bytes_per_cell_step() * value / 1e9,
                 "step_effective_frac": bytes_per_cell_step() * value / 1e9 / peak}
 
+    # ---- variant: non-zero viscosity / diffusivity (general divisor c = 1 + 4a in the three diffusion solves) ----
+    def timed_steps(visc, diff, n):
+        for _ in range(3):
+            _lib.check(L.fruid_fluid_step(sim._h, DT, visc))
+            _lib.check(L.fruid_density_step_dev(den._h, sim._h, DT, diff))
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(n):
+            _lib.check(L.fruid_fluid_step(sim._h, DT, visc))
+            _lib.check(L.fruid_density_step_dev(den._h, sim._h, DT, diff))
+        a1.record(stream)
+        torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / n
+    vms = timed_steps(1e-6, 1e-6, max(2, min(args.steps, 10)))
+    variant = {"visc": 1e-6, "diff": 1e-6, "ms_per_step": vms, "value": w * h / (vms * 1e-3), "unit": "cell-steps/s",
+               "note": "same scene with visc = diff = 1e-6 (SURVEY.md 8d config 1 variant B): the diffusion solves divide by "
+                       "c = 1 + 4a through the verified reciprocal path"}
+
     # ---- end to end through the crate-API mirror with HOST buffers ----
     e2e = run_e2e(args, fb, torch, sc, w, h)
 
@@ -313,7 +332,7 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1),
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "impl": "b200"}
+            "cpu_baseline": cpu, "impl": "b200", "variant_viscous": variant}
     print(json.dumps(line), flush=True)
 
 

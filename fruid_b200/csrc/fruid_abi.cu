@@ -456,7 +456,7 @@ struct FieldSet {
         if (base) cudaFree(base);
         if (slab.adv_block_flag) cudaFree(slab.adv_block_flag);
         if (ev) cudaEventDestroy(ev);
-        if (stream) cudaStreamDestroy(stream);
+        if (stream) { tile_sched_release(stream); cudaStreamDestroy(stream); }
     }
     // Host arrays cover the rows this rank OWNS (the whole field on one GPU), dense w floats per row.
     int upload(int field, const float* host) {

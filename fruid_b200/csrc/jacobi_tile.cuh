@@ -585,6 +585,14 @@ static inline int tiles_needed(int extent, int tile, int stride) {
     return (extent - tile + stride - 1) / stride + 1;
 }
 
+static void tile_sched_release(cudaStream_t st) {  // the stream is going away (handle destroyed)
+    std::lock_guard<std::mutex> lk(g_sched_mu);
+    auto it = g_sched.find(st);
+    if (it == g_sched.end()) return;
+    cudaFree(it->second);
+    g_sched.erase(it);
+}
+
 static inline int jacobi_tile_max_T(int R, int NW) {
     const int th = R * NW;
     int H = (th < 128 ? th : 128) / 2 - 2;  // keep at least 4 output rows/cols per tile
