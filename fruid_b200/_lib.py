@@ -83,6 +83,7 @@ SIGNATURES = {
     "fruid_density_set_iterations": [_vp, _i],
     "fruid_density_set_fused_sweeps": [_vp, _i],
     "fruid_density_step_dev": [_vp, _vp, _f, _f],
+    "fruid_density_step_dev_batch": [_vp, _i, _vp, _f, _f],
     "fruid_density_step_host": [_vp, _vp, _vp, _f, _f],
     "fruid_density_sync": [_vp],
     "fruid_draw_density": [_vp, _vp, _vp, _vp, _f, _vp],

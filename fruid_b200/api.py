@@ -227,6 +227,29 @@ class DensitySim:
         self._dens._mark_stale()
         self._dens_prev._mark_stale()
 
+    @staticmethod
+    def step_all(dyes, uv, dt: float, diff: float) -> None:
+        """`for d in dyes: d.step(uv, dt, diff)` (main.rs:114-118) as one batched call when `uv` is a
+        FluidSim's device-resident uv(); same results bit for bit."""
+        dyes = list(dyes)
+        u, v = uv
+        sim = getattr(u, "_owner", None)
+        if not (len(dyes) > 1 and isinstance(u, Array2D) and isinstance(v, Array2D) and isinstance(sim, FluidSim)
+                and v._owner is sim and u._field == _lib.U and v._field == _lib.V):
+            for d in dyes:
+                d.step(uv, dt, diff)
+            return
+        for d in dyes:
+            d._dens._push()
+            d._dens_prev._push()
+        u._push()
+        v._push()
+        handles = (_lib._vp * len(dyes))(*[d._h for d in dyes])
+        check(lib.fruid_density_step_dev_batch(handles, len(dyes), sim._h, dt, diff))
+        for d in dyes:
+            d._dens._mark_stale()
+            d._dens_prev._mark_stale()
+
     def density(self) -> Array2D:  # lib.rs:238
         return self._dens
 

@@ -238,7 +238,7 @@ static int op_add_source_diffuse(int b, float*& x, float* x0, float*& scratch, f
     return op_lin_solve(b, x, x0, scratch, g, a, c, iters, fused, st, false, true, dt, z_tmp);
 }
 
-// advect, src/lib.rs:84-126, for 1 or 2 fields sharing the back-trace.  `tab` (slab mode) says where
+// advect, src/lib.rs:84-126, for 1..4 fields sharing the back-trace (slab mode: 1 or 2).  `tab` (slab mode) says where
 // the rows of the gathered fields live on the other ranks; d0[] must then be indexed by GLOBAL row
 // and [ly0, ly1) are the local rows to produce (default: every interior row).
 static int op_advect(int nf, float* const* d, const float* const* d0, const int* b, const float* u, const float* v,
@@ -263,11 +263,16 @@ static int op_advect(int nf, float* const* d, const float* const* d0, const int*
     const dim3 grid1(((g.w + 3) / 4 + 31) / 32, (ly1 - ly0 + 7) / 8);
     SlabTable T = *tab;
     T.grid_x = (int)grid1.x;
-    if (multi) CU(cudaMemsetAsync(T.block_list, 0, sizeof(int), st));  // empty work list for pass 2
 #define FRUID_ADVECT(NF, PASS, name) \
     LAUNCH(name, st, (k_advect4<NF, PASS><<<(PASS == 2 ? dim3(296) : grid1), vec_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, T)))
+    if (nf < 1 || nf > ADVECT_MAX_FIELDS || (multi && nf > 2)) return fail(FRUID_ERR_BAD_ARG, "advect: unsupported field count %d", nf);
     if (!multi) {
-        if (nf == 2) FRUID_ADVECT(2, 0, "k_advect4x2"); else FRUID_ADVECT(1, 0, "k_advect4x1");
+        switch (nf) {
+            case 1: FRUID_ADVECT(1, 0, "k_advect4x1"); break;
+            case 2: FRUID_ADVECT(2, 0, "k_advect4x2"); break;
+            case 3: FRUID_ADVECT(3, 0, "k_advect4x3"); break;
+            default: FRUID_ADVECT(4, 0, "k_advect4x4"); break;
+        }
     } else {  // pass 1: cells whose taps are all local; pass 2: the rest, from the owners' memory
         if (nf == 2) { FRUID_ADVECT(2, 1, "k_advect4x2"); FRUID_ADVECT(2, 2, "k_advect4x2_remote"); }
         else { FRUID_ADVECT(1, 1, "k_advect4x1"); FRUID_ADVECT(1, 2, "k_advect4x1_remote"); }
@@ -345,6 +350,7 @@ struct StepGraph {
     int iters = 0, fused = 0;
     const void* a0 = nullptr;      // density: the velocity pointers the graph was captured with
     const void* a1 = nullptr;
+    std::vector<const void*> extra;  // batched dye step: the participating handles
     uint64_t kernels = 0;          // kernel launches inside the graph
     int cfg_epoch = -1;            // value of g_cfg_epoch the parameters were recorded under
     bool failed = false;           // capture did not work for these parameters: stay on direct launches
@@ -360,6 +366,8 @@ static bool g_graphs_enabled = true;
 
 struct FieldSet {
     StepGraph graph;
+    StepGraph batch_graph;                       // fruid_density_step_dev_batch led by this handle
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // fork / join of the batched step (also inside captures)
     Geom g{};
     int n = 0;       // buffers allocated: user fields, then scratch (lib.rs:213,252), then the add_source temporary
     int n_user = 0;  // fields the crate API exposes
@@ -428,6 +436,8 @@ struct FieldSet {
         n_user = nfields - 2;
         CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         field_bytes = g.pitch * (size_t)g.h * sizeof(float);
         // slab mode: outbox = 2 parities x 4 field slots x 2 directions x SLAB_HALO rows (halo exchange staging)
         const size_t total = SLAB_FLAG_BYTES + (size_t)n * field_bytes + (world > 1 ? 16 * outbox_slot_bytes() : 0);
@@ -441,6 +451,7 @@ struct FieldSet {
     void release() {
         if (stream) cudaStreamSynchronize(stream);
         graph.reset();
+        batch_graph.reset();
         for (int r = 0; r < slab.world; ++r)
             if (r != slab.rank && slab.peer_base[r]) cudaIpcCloseMemHandle(slab.peer_base[r]);
         if (copy_stream) cudaStreamSynchronize(copy_stream);
@@ -456,6 +467,8 @@ struct FieldSet {
         if (base) cudaFree(base);
         if (slab.adv_block_flag) cudaFree(slab.adv_block_flag);
         if (ev) cudaEventDestroy(ev);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
         if (stream) { tile_sched_release(stream); cudaStreamDestroy(stream); }
     }
     // Host arrays cover the rows this rank OWNS (the whole field on one GPU), dense w floats per row.
@@ -597,9 +610,11 @@ struct FieldSet {
         return 0;
     }
     // Halo exchange of up to 4 fields: publish my boundary rows in my outbox, pull the neighbours'.
-    int exchange(std::initializer_list<float*> fields) {
+    int exchange(std::initializer_list<float*> fields, int wait_adv_event = 0) {
         if (!is_slab()) return 0;
         PullArgs A{};
+        A.wait_adv_event = wait_adv_event;
+        A.world = slab.world;
         const int me = slab.rank;
         A.me = me; A.pitch = g.pitch; A.event = ++slab.ev_pull;
         A.nbr[0] = me > 0 ? me - 1 : -1;
@@ -675,12 +690,14 @@ struct FieldSet {
         const size_t blocks = (size_t)(((g.w + 3) / 4 + 31) / 32) * (size_t)((g.h + 7) / 8);
         if (blocks > slab.adv_blocks) {
             if (slab.adv_block_flag) CU(cudaFree(slab.adv_block_flag));
-            CU(cudaMalloc(&slab.adv_block_flag, (2 * blocks + 1) * sizeof(int)));  // flags, then the pass-2 work list
-            CU(cudaMemsetAsync(slab.adv_block_flag, 0, (2 * blocks + 1) * sizeof(int), stream));
+            CU(cudaMalloc(&slab.adv_block_flag, (2 * blocks + 2) * sizeof(int)));  // flags, pass-2 work list, pass-2 block counter
+            CU(cudaMemsetAsync(slab.adv_block_flag, 0, (2 * blocks + 2) * sizeof(int), stream));
             slab.adv_blocks = blocks;
         }
         t.block_flag = slab.adv_block_flag;
         t.block_list = slab.adv_block_flag + slab.adv_blocks;
+        t.pass2_done = slab.adv_block_flag + 2 * slab.adv_blocks + 1;
+        for (int r = 0; r < slab.world; ++r) t.flags[r] = flags(r);
         t.src_done = flags(slab.rank)->src_done;
         t.error = &flags(slab.rank)->error;
         t.event = slab.ev_adv;
@@ -730,8 +747,7 @@ static int op_vel_step_slab(FieldSet& S, float visc, float dt) {
     TRY(S.exchange({u0, v0}));
     TRY(S.wait_readers());                     // density steps of the previous scene step have read u, v
     TRY(project_slab(S, u0, v0, u, v, T));                                             // lib.rs:199 (overwrites u, v)
-    S.slab.ev_adv += 1;
-    TRY(S.signal_all(0));                      // my u0, v0 are final: owners' rows may be gathered
+    S.slab.ev_adv += 1;                        // advect pass 1 broadcasts "my u0, v0 are final" (src_done)
     {
         SlabTable tab{};
         TRY(S.fill_table(tab, 0, u0));
@@ -742,9 +758,9 @@ static int op_vel_step_slab(FieldSet& S, float visc, float dt) {
         const int ly0 = std::max(S.own_lo(), 1 - g.gy0), ly1 = std::min(S.own_hi(), g.gh - 1 - g.gy0);
         TRY(op_advect(2, d, d0, b, u0, v0, g, dt, st, &tab, ly0, ly1));                // lib.rs:204-205
     }
-    TRY(S.signal_all(1));                      // I have stopped reading everybody's u0, v0
-    TRY(S.exchange({u, v}));
-    TRY(S.wait_all(1, S.slab.ev_adv));         // everybody has: project may overwrite u0, v0 (as p, div)
+    // advect pass 2 broadcast "I have stopped reading everybody's u0, v0" (adv_done); the exchange below also
+    // waits until everybody has, because the projection overwrites u0, v0 (as p, div)
+    TRY(S.exchange({u, v}, S.slab.ev_adv));
     return project_slab(S, u, v, u0, v0, T);                                           // lib.rs:207
 }
 
@@ -759,12 +775,10 @@ static int op_dens_step_slab(FieldSet& S, const float* u, const float* v, float 
     float *&x = S.buf[0], *&x0 = S.buf[1], *&s = S.buf[2];
     float* const s2 = S.buf[3];
     const float a = ((dt * diff) * (float)g.nx) * (float)g.ny, c = 1.0f + 4.0f * a;
-    TRY(S.wait_all(1, S.slab.ev_adv));         // everybody has finished the previous advect's reads of x0
-    TRY(S.exchange({x, x0}));
+    TRY(S.exchange({x, x0}, S.slab.ev_adv));   // ... and everybody has finished the previous advect's reads of x0
     SlabSolve sd{SLAB_HALO, SLAB_HALO, 0, [&S](std::initializer_list<float*> f) { return S.exchange(f); }};
     TRY(op_lin_solve(B_POSITIVE, x0, x, s, g, a, c, S.iters, T, st, false, true, dt, s2, &sd));  // lib.rs:172,175
-    S.slab.ev_adv += 1;
-    TRY(S.signal_all(0));                      // my x0 is final
+    S.slab.ev_adv += 1;                        // advect pass 1 broadcasts "my x0 is final"
     CU(cudaStreamWaitEvent(st, vel_ready, 0)); // u, v of this step
     SlabTable tab{};
     TRY(S.fill_table(tab, 0, x0));
@@ -772,8 +786,7 @@ static int op_dens_step_slab(FieldSet& S, const float* u, const float* v, float 
     const float* d0[1] = {S.global_rows(x0)};
     const int b[1] = {B_POSITIVE};
     const int ly0 = std::max(S.own_lo(), 1 - g.gy0), ly1 = std::min(S.own_hi(), g.gh - 1 - g.gy0);
-    TRY(op_advect(1, d, d0, b, u, v, g, dt, st, &tab, ly0, ly1));                       // lib.rs:178
-    return S.signal_all(1);                    // I have stopped reading everybody's x0
+    return op_advect(1, d, d0, b, u, v, g, dt, st, &tab, ly0, ly1);                     // lib.rs:178 (pass 2 broadcasts adv_done)
 }
 
 // Runs `body` (which enqueues one step on S.stream) either directly or as a replayed CUDA graph.
@@ -781,15 +794,16 @@ static int op_dens_step_slab(FieldSet& S, const float* u, const float* v, float 
 // and only kept if the step left the buffer roles unchanged (an even number of launches per
 // lin_solve), because the graph bakes the pointers in.
 template <class Body>
-static int run_step_graphed(FieldSet& S, float dt, float p, const void* a0, const void* a1, Body body) {
-    StepGraph& G = S.graph;
-    const bool usable = g_graphs_enabled && !g_prof_on && !S.is_slab();
+static int run_graphed(StepGraph& G, FieldSet& S, const std::vector<FieldSet*>& parts, float dt, float p, const void* a0,
+                       const void* a1, const std::vector<const void*>& extra, Body body) {
+    bool usable = g_graphs_enabled && !g_prof_on;
+    for (FieldSet* P : parts) usable &= !P->is_slab();
     if (!usable) return body();
-    if (!G.matches(dt, p, S.iters, S.fused, a0, a1)) {
+    if (!G.matches(dt, p, S.iters, S.fused, a0, a1) || G.extra != extra) {
         // first step with these parameters: run it directly (it warms lazy allocations, tensor maps and
         // the divisor check, none of which may happen inside a capture) and remember the parameters
         G.reset();
-        G.dt = dt; G.p = p; G.iters = S.iters; G.fused = S.fused; G.a0 = a0; G.a1 = a1;
+        G.dt = dt; G.p = p; G.iters = S.iters; G.fused = S.fused; G.a0 = a0; G.a1 = a1; G.extra = extra;
         G.cfg_epoch = g_cfg_epoch.load();
         return body();
     }
@@ -800,8 +814,10 @@ static int run_step_graphed(FieldSet& S, float dt, float p, const void* a0, cons
     }
     if (G.failed) return body();
     // second step with the same parameters: capture it
-    float* before[6];
-    for (int i = 0; i < 6; ++i) before[i] = S.buf[i];
+    std::vector<float*> before;
+    for (FieldSet* P : parts) before.insert(before.end(), P->buf, P->buf + 6);
+    auto restore = [&]() { size_t k = 0; for (FieldSet* P : parts) for (int i = 0; i < 6; ++i) P->buf[i] = before[k++]; };
+    auto unchanged = [&]() { size_t k = 0; bool same = true; for (FieldSet* P : parts) for (int i = 0; i < 6; ++i) same &= (P->buf[i] == before[k++]); return same; };
     const uint64_t k0 = g_launches.load();
     if (cudaStreamBeginCapture(S.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
         cudaGetLastError();
@@ -813,13 +829,11 @@ static int run_step_graphed(FieldSet& S, float dt, float p, const void* a0, cons
     const cudaError_t e = cudaStreamEndCapture(S.stream, &graph);
     const uint64_t nk = g_launches.load() - k0;
     g_launches.fetch_sub(nk, std::memory_order_relaxed);  // nothing has run yet
-    bool same = true;
-    for (int i = 0; i < 6; ++i) same &= (before[i] == S.buf[i]);
-    if (r != 0 || e != cudaSuccess || !graph || !same ||
+    if (r != 0 || e != cudaSuccess || !graph || !unchanged() ||
         cudaGraphInstantiate(&G.exec, graph, nullptr, nullptr, 0) != cudaSuccess) {
         cudaGetLastError();
         if (graph) cudaGraphDestroy(graph);
-        for (int i = 0; i < 6; ++i) S.buf[i] = before[i];
+        restore();
         G.exec = nullptr;
         G.failed = true;
         return body();  // the captured work was never launched: run the step directly
@@ -829,6 +843,10 @@ static int run_step_graphed(FieldSet& S, float dt, float p, const void* a0, cons
     CU(cudaGraphLaunch(G.exec, S.stream));
     g_launches.fetch_add(nk, std::memory_order_relaxed);
     return 0;
+}
+template <class Body>
+static int run_step_graphed(FieldSet& S, float dt, float p, const void* a0, const void* a1, Body body) {
+    return run_graphed(S.graph, S, {&S}, dt, p, a0, a1, {}, body);
 }
 // Tuning / debugging knob: replay steps as CUDA graphs (default on).
 extern "C" int fruid_set_graphs_enabled(int on) { g_graphs_enabled = on != 0; g_cfg_epoch.fetch_add(1); return 0; }
@@ -995,6 +1013,76 @@ extern "C" int fruid_density_step_dev(fruid_density_t* d, fruid_fluid_t* vel, fl
     } else {
         CU(cudaStreamWaitEvent(vs.stream, s.ev, 0));
     }
+    return 0;
+}
+// Several dye fields advanced by one velocity field (the four DensitySims of main.rs:114-118): every
+// dye's add_source + diffuse runs on its own stream (concurrently on small grids), then ONE advect
+// launch moves up to four dyes with a shared back-trace (u, v are read once instead of once per dye).
+// Results are those of n separate fruid_density_step_dev calls, bit for bit.
+static int dens_step_batch_body(const std::vector<FieldSet*>& D, FieldSet& V, float dt, float diff) {
+    FieldSet& L = *D[0];
+    CU(cudaEventRecord(L.ev_fork, L.stream));
+    for (size_t i = 0; i < D.size(); ++i) {
+        FieldSet& s = *D[i];
+        if (i) CU(cudaStreamWaitEvent(s.stream, L.ev_fork, 0));
+        TRY(op_add_source_diffuse(B_POSITIVE, s.buf[1], s.buf[0], s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream));  // lib.rs:172,175
+        if (i) {
+            CU(cudaEventRecord(s.ev_join, s.stream));
+            CU(cudaStreamWaitEvent(L.stream, s.ev_join, 0));
+        }
+    }
+    for (size_t i0 = 0; i0 < D.size(); i0 += ADVECT_MAX_FIELDS) {
+        const int nf = (int)std::min<size_t>(ADVECT_MAX_FIELDS, D.size() - i0);
+        float* d[ADVECT_MAX_FIELDS];
+        const float* d0[ADVECT_MAX_FIELDS];
+        int b[ADVECT_MAX_FIELDS];
+        for (int f = 0; f < nf; ++f) { d[f] = D[i0 + f]->buf[0]; d0[f] = D[i0 + f]->buf[1]; b[f] = B_POSITIVE; }
+        TRY(op_advect(nf, d, d0, b, V.buf[0], V.buf[1], L.g, dt, L.stream));  // lib.rs:178
+    }
+    return 0;
+}
+extern "C" int fruid_density_step_dev_batch(fruid_density_t* const* dyes, int n, fruid_fluid_t* vel, float dt, float diff) {
+    if (!dyes || n < 0) return fail(FRUID_ERR_BAD_ARG, "null dye array or negative count");
+    if (!vel) return fail(FRUID_ERR_BAD_ARG, "null velocity handle");
+    if (n == 0) return 0;
+    for (int i = 0; i < n; ++i) {
+        if (!dyes[i]) return fail(FRUID_ERR_BAD_ARG, "null handle (dye %d)", i);
+        for (int k = 0; k < i; ++k)
+            if (dyes[k] == dyes[i]) return fail(FRUID_ERR_BAD_ARG, "dye %d given twice", i);
+    }
+    FieldSet& L = dyes[0]->s;
+    FieldSet& V = vel->s;
+    bool batchable = !L.is_slab() && !V.is_slab() && n > 1;
+    for (int i = 1; i < n; ++i) batchable &= dyes[i]->s.iters == L.iters && dyes[i]->s.fused == L.fused && !dyes[i]->s.is_slab();
+    if (!batchable) {  // slab-decomposed or differently configured dyes: one step each (same results)
+        for (int i = 0; i < n; ++i) TRY(fruid_density_step_dev(dyes[i], vel, dt, diff));
+        return 0;
+    }
+    CU(cudaSetDevice(L.device));
+    std::vector<FieldSet*> D;
+    std::vector<const void*> key;
+    for (int i = 0; i < n; ++i) {
+        FieldSet& s = dyes[i]->s;
+        if (V.g.w != s.g.w || V.g.gh != s.g.gh)
+            return fail(FRUID_ERR_SIZE_MISMATCH, "density %dx%d vs velocity %dx%d", s.g.w, s.g.gh, V.g.w, V.g.gh);
+        if (s.device != V.device) return fail(FRUID_ERR_BAD_ARG, "density and velocity live on different devices");
+        TRY(s.consume_uploads());
+        D.push_back(&s);
+        key.push_back(&s);
+    }
+    // Everything is driven from the first dye's stream: it waits for the velocity step and for whatever
+    // is still queued on the other dyes' streams (uploads, injects, fills) ...
+    CU(cudaEventRecord(V.ev, V.stream));
+    CU(cudaStreamWaitEvent(L.stream, V.ev, 0));
+    for (int i = 1; i < n; ++i) {
+        CU(cudaEventRecord(D[i]->ev, D[i]->stream));
+        CU(cudaStreamWaitEvent(L.stream, D[i]->ev, 0));
+    }
+    TRY(run_graphed(L.batch_graph, L, D, dt, diff, V.buf[0], V.buf[1], key, [&]() { return dens_step_batch_body(D, V, dt, diff); }));
+    // ... and the other dyes' streams and the velocity stream continue after it.
+    CU(cudaEventRecord(L.ev, L.stream));
+    for (int i = 1; i < n; ++i) CU(cudaStreamWaitEvent(D[i]->stream, L.ev, 0));
+    CU(cudaStreamWaitEvent(V.stream, L.ev, 0));
     return 0;
 }
 extern "C" int fruid_density_step_host(fruid_density_t* d, const float* u, const float* v, float dt, float diff) {

@@ -104,10 +104,12 @@ __device__ __forceinline__ float gather(const float* __restrict__ d0, const Geom
 // advect, src/lib.rs:84-126 (+ set_bnd at :125), for NF fields sharing one back-trace:
 // NF = 2 is the velocity self-advection of lib.rs:204-205 (d0 aliases u / v), NF = 1 the
 // density advection of lib.rs:178.
+// NF = 3, 4: several dye fields advected by one velocity (the four DensitySims of main.rs:114-118).
+constexpr int ADVECT_MAX_FIELDS = 4;
 struct AdvectArgs {
-    float* d[2];
-    const float* d0[2];
-    int b[2];
+    float* d[ADVECT_MAX_FIELDS];
+    const float* d0[ADVECT_MAX_FIELDS];
+    int b[ADVECT_MAX_FIELDS];
 };
 template <int NF>
 __global__ void k_advect(AdvectArgs a, const float* __restrict__ u, const float* __restrict__ v, Geom g, float dt0,

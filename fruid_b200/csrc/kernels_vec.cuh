@@ -149,6 +149,8 @@ struct SlabTable {
     const int* src_done;       // my SlabFlags::src_done[]: src_done[r] >= event <=> rank r's fields are final
     int* error;
     int event;
+    SlabFlags* flags[8];       // every rank's flag block (peer-mapped): pass 1 broadcasts src_done, pass 2 adv_done
+    int* pass2_done;           // block counter of pass 2 (self-resetting)
 };
 __device__ __forceinline__ int slab_owner(const SlabTable& t, int gj) {
     int r = 0;  // branch-free: number of slab cuts at or below gj
@@ -248,11 +250,19 @@ template <int NF, int PASS>
 __global__ void k_advect4(AdvectArgs a, const float* __restrict__ u, const float* __restrict__ v, Geom g, float dt0,
                           float dt1, float xmax, float ymax, int ly0, int ly1, const __grid_constant__ SlabTable tab) {
     if (PASS != 2) {
+        // Folded "src_done" broadcast: the kernels that wrote the gathered fields precede this launch in
+        // stream order, so they are final; tell every rank (nobody waits here).
+        if (PASS == 1 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.y == 0 && (int)threadIdx.x < tab.world)
+            st_release_sys(&tab.flags[threadIdx.x]->src_done[tab.me], tab.event);
         advect4_block<NF, PASS>(a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, tab, blockIdx.x, blockIdx.y);
         return;
     }
     const int count = tab.block_list[0];
-    if (count == 0) return;
+    if (count == 0) {  // nothing was gathered remotely: "adv_done" can be broadcast right away
+        if (blockIdx.x == 0 && threadIdx.y == 0 && (int)threadIdx.x < tab.world)
+            st_release_sys(&tab.flags[threadIdx.x]->adv_done[tab.me], tab.event);
+        return;
+    }
     if (threadIdx.x == 0 && threadIdx.y == 0) {
         // One thread waits (system-scope acquire) for the two NEIGHBOUR owners on behalf of the block --
         // a system fence per thread would serialise; farther owners are handled per thread.
@@ -264,6 +274,16 @@ __global__ void k_advect4(AdvectArgs a, const float* __restrict__ u, const float
         const int bid = tab.block_list[1 + i];
         if (threadIdx.x == 0 && threadIdx.y == 0) tab.block_flag[bid] = 0;
         advect4_block<NF, 2>(a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, tab, bid % tab.grid_x, bid / tab.grid_x);
+    }
+    // Folded "adv_done" broadcast by the last block to finish: this rank no longer reads anybody's fields.
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        __threadfence();
+        if (atomicAdd(tab.pass2_done, 1) == (int)gridDim.x - 1) {
+            *tab.pass2_done = 0;
+            tab.block_list[0] = 0;  // everybody has read the count: leave an empty work list for the next advect
+            for (int r = 0; r < tab.world; ++r) st_release_sys(&tab.flags[r]->adv_done[tab.me], tab.event);
+        }
     }
 }
 

@@ -83,6 +83,8 @@ struct PullArgs {
     int nbr[2];            // neighbour ranks (-1 = none): up, down
     SlabFlags* mine;       // my flag block
     SlabFlags* peer[2];    // neighbours' flag blocks (peer-mapped)
+    int wait_adv_event;    // > 0: before returning, also wait until every rank's adv_done >= this epoch
+    int world;
 };
 
 __device__ __forceinline__ void copy_rows4(float4* dst, const float4* src, size_t n4, bool peer) {
@@ -126,6 +128,10 @@ __global__ void k_slab_pull(const __grid_constant__ PullArgs A) {
     __syncthreads();
     if (s_ok && j.in_rows > 0)
         copy_rows4(reinterpret_cast<float4*>(j.dst), reinterpret_cast<const float4*>(j.src), (size_t)j.in_rows * A.pitch / 4, true);
+    // Folded k_slab_wait_all: whatever follows this exchange may overwrite fields that other ranks gathered
+    // from during their advect; the flags were broadcast long ago, so this normally costs one load each.
+    if (A.wait_adv_event > 0 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < A.world && (int)threadIdx.x != A.me)
+        spin_until(&mine->adv_done[threadIdx.x], A.wait_adv_event, &mine->error);
 }
 
 // "Lazy" all-rank synchronisation around the peer gathers of advect: instead of two barriers,

@@ -16,7 +16,9 @@ F = np.float32
 class Scene:
     """The default scene: one FluidSim + four dye DensitySims (c, m, y, k)."""
 
-    def __init__(self, fluid_cls, density_cls, width: int = 250, height: int = 250, n_dyes: int = 4):
+    def __init__(self, fluid_cls, density_cls, width: int = 250, height: int = 250, n_dyes: int = 4,
+                 batched: bool = True):
+        self.batched = batched
         self.sim = fluid_cls(width, height)                       # main.rs:36
         self.dyes = [density_cls(self.sim.width(), self.sim.height()) for _ in range(n_dyes)]  # main.rs:38
         self.frame_count = 0
@@ -28,8 +30,16 @@ class Scene:
         for d, (x, val) in zip(self.dyes, place):
             d.density_mut()[(x, h // 2)] = val
         self.sim.step(0.1, 0.0)                                   # main.rs:48
-        for d in self.dyes:                                       # main.rs:49-52
-            d.step(self.sim.uv(), 0.1, 0.0)
+        self._step_dyes(0.1, 0.0)                                 # main.rs:49-52
+
+    def _step_dyes(self, dt: float, diff: float) -> None:
+        """`d.step(sim.uv(), dt, diff)` for every dye; batched when the implementation offers it."""
+        step_all = getattr(type(self.dyes[0]), "step_all", None) if self.batched and self.dyes else None
+        if step_all is not None:
+            step_all(self.dyes, self.sim.uv(), dt, diff)
+        else:
+            for d in self.dyes:
+                d.step(self.sim.uv(), dt, diff)
 
     def injection(self):
         """(pos, u_val, v_val) for the current frame_count, main.rs:92-102."""
@@ -51,8 +61,7 @@ class Scene:
         for d in self.dyes:                                       # main.rs:105-108
             d.density_mut().fill(0.0)
         self.sim.step(dt, visc)                                   # main.rs:114
-        for d in self.dyes:                                       # main.rs:115-118
-            d.step(self.sim.uv(), dt, diff)
+        self._step_dyes(dt, diff)                                 # main.rs:115-118
 
     def run(self, frames: int, **kw) -> None:
         for _ in range(frames):

@@ -21,6 +21,7 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <initializer_list>
 #include <vector>
 
 #include "fruid_b200.h"
@@ -121,6 +122,13 @@ public:
         push();
         check(fruid_density_step_host(h_, uv.first.data().data(), uv.second.data().data(), dt, diff));
         dens_stale_ = prev_stale_ = true;
+    }
+    // c.step(sim.uv(), ..); m.step(sim.uv(), ..); ... (main.rs:114-118) as one batched call.
+    static void step_all(std::initializer_list<DensitySim*> dyes, FluidSim& vel, float dt, float diff) {
+        std::vector<fruid_density_t*> h;
+        for (DensitySim* d : dyes) { d->push(); h.push_back(d->h_); }
+        check(fruid_density_step_dev_batch(h.data(), (int)h.size(), vel.handle(), dt, diff));
+        for (DensitySim* d : dyes) d->dens_stale_ = d->prev_stale_ = true;
     }
     const Array2D& density() {  // lib.rs:238
         if (dens_stale_) {

@@ -129,6 +129,11 @@ int fruid_density_set_fused_sweeps(fruid_density_t *d, int t);
 /* DensitySim::step((u, v), dt, diff), src/lib.rs:226-236 -> dens_step src/lib.rs:171-179,
  * with (u, v) = vel's device-resident uv() (the `c.step(sim.uv(), ..)` pattern, src/main.rs:115). */
 int fruid_density_step_dev(fruid_density_t *d, fruid_fluid_t *vel, float dt, float diff);
+/* The caller pattern of src/main.rs:114-118 -- several DensitySims stepped with the same sim.uv():
+ *     c.step(sim.uv(), dt, diff); m.step(sim.uv(), dt, diff); y.step(...); k.step(...);
+ * as one call.  Results are those of n fruid_density_step_dev calls, bit for bit; the dyes'
+ * diffuses run concurrently and one advect launch moves up to four dyes with a shared back-trace. */
+int fruid_density_step_dev_batch(fruid_density_t *const *dyes, int n, fruid_fluid_t *vel, float dt, float diff);
 /* Same, with (u, v) given as host arrays (uploaded first). */
 int fruid_density_step_host(fruid_density_t *d, const float *u, const float *v, float dt, float diff);
 int fruid_density_sync(fruid_density_t *d);

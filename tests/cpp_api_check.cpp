@@ -12,6 +12,8 @@ int main() {
         c.density_mut()[{20, 24}] = 80.0f * 64 * 48;
         sim.step(0.1f, 0.0f);
         c.step(sim, 0.1f, 0.0f);
+        fruid::DensitySim m(sim.width(), sim.height());
+        fruid::DensitySim::step_all({&c, &m}, sim, 1e-2f, 0.0f);  // main.rs:114-118, batched
         auto [u, v] = sim.uv();
         double s = 0;
         for (float x : u.data()) s += x;

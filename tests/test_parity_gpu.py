@@ -248,6 +248,92 @@ def test_reference_scene_checksums(fb, key, w, h, frames):
         assert hashlib.sha256(a.tobytes()).hexdigest() == sums["sha256"][k], k
 
 
+def test_reference_scene_unbatched_dyes_vs_golden(fb):
+    """The same scene with one fruid_density_step_dev per dye (the literal main.rs:115-118 sequence)."""
+    from fruid_b200.scene import Scene
+    g = np.load(os.path.join(GOLD, "scene_64x48_f6.npz"))
+    s = Scene(fb.FluidSim, fb.DensitySim, 64, 48, batched=False)
+    s.run(6)
+    for k, a in _scene_fields(s).items():
+        assert_bits(a, g[k], k)
+
+
+@pytest.mark.parametrize("w,h", [(2, 2), (3, 7), (61, 45), (250, 250), (300, 140)])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 9])
+@pytest.mark.parametrize("diff", [0.0, 3e-4])
+def test_batched_dye_steps_match_the_oracle(fb, oracle_mod, w, h, n, diff):
+    """`for d in dyes: d.step(sim.uv(), dt, diff)` (main.rs:114-118) as one
+    fruid_density_step_dev_batch call -- direct, captured and replayed steps, against the oracle."""
+    rng = np.random.default_rng(w * 131 + h * 7 + n)
+    sim, osim = fb.FluidSim(w, h), oracle_mod.Fluid(w, h)
+    for name, field in (("u", 0), ("v", 1)):
+        a = rand_field(rng, w, h, 6.0)
+        getattr(osim, name)[:] = a
+        fb._lib.check(fb._lib.lib.fruid_fluid_upload(sim._h, field, fb._lib.ptr(a)))
+    dyes = [fb.DensitySim(w, h) for _ in range(n)]
+    odyes = [oracle_mod.Density(w, h) for _ in range(n)]
+    for d, od in zip(dyes, odyes):
+        a, b = rand_field(rng, w, h), rand_field(rng, w, h)
+        od.dens[:] = a
+        od.dens_prev[:] = b
+        fb._lib.check(fb._lib.lib.fruid_density_upload(d._h, 0, fb._lib.ptr(a)))
+        fb._lib.check(fb._lib.lib.fruid_density_upload(d._h, 1, fb._lib.ptr(b)))
+    for step in range(4):
+        if step == 2:  # a source written between batched steps must reach the device (main.rs:43)
+            dyes[-1].density_mut()[(w // 2, h // 2)] = 7.5
+            odyes[-1].dens_prev[h // 2, w // 2] = 7.5
+        fb.DensitySim.step_all(dyes, sim.uv(), 0.05, diff)
+        for od in odyes:
+            od.step((osim.u, osim.v), 0.05, diff)
+    for i, (d, od) in enumerate(zip(dyes, odyes)):
+        assert_bits(d.density().numpy(), od.dens, f"dens{i}")
+        assert_bits(d.density_mut().numpy(), od.dens_prev, f"dens_prev{i}")
+
+
+def test_batched_and_single_dye_steps_interleave(fb, oracle_mod):
+    """Batched and per-dye steps may be mixed on the same handles (each keeps its own captured graph),
+    also with a velocity step in between."""
+    w, h = 130, 70
+    rng = np.random.default_rng(99)
+    sim, osim = fb.FluidSim(w, h), oracle_mod.Fluid(w, h)
+    for name, field in (("u_prev", 2), ("v_prev", 3)):
+        a = rand_field(rng, w, h, 40.0)
+        getattr(osim, name)[:] = a
+        fb._lib.check(fb._lib.lib.fruid_fluid_upload(sim._h, field, fb._lib.ptr(a)))
+    dyes = [fb.DensitySim(w, h) for _ in range(3)]
+    odyes = [oracle_mod.Density(w, h) for _ in range(3)]
+    for d, od in zip(dyes, odyes):
+        a = rand_field(rng, w, h)
+        od.dens_prev[:] = a
+        fb._lib.check(fb._lib.lib.fruid_density_upload(d._h, 1, fb._lib.ptr(a)))
+    for step in range(6):
+        sim.step(0.02, 0.0)
+        osim.step(0.02, 0.0)
+        if step % 3 == 2:
+            for d in dyes:
+                d.step(sim.uv(), 0.02, 0.0)
+        else:
+            fb.DensitySim.step_all(dyes if step % 2 else dyes[::-1], sim.uv(), 0.02, 0.0)
+        for od in odyes:
+            od.step((osim.u, osim.v), 0.02, 0.0)
+    for i, (d, od) in enumerate(zip(dyes, odyes)):
+        assert_bits(d.density().numpy(), od.dens, f"dens{i}")
+        assert_bits(d.density_mut().numpy(), od.dens_prev, f"dens_prev{i}")
+
+
+def test_batched_dye_step_errors(fb):
+    L = fb._lib
+    sim = fb.FluidSim(40, 30)
+    a, b, c = fb.DensitySim(40, 30), fb.DensitySim(40, 30), fb.DensitySim(41, 30)
+    arr = lambda *ds: (L._vp * len(ds))(*[d._h for d in ds])
+    assert L.lib.fruid_density_step_dev_batch(arr(a, b), 2, sim._h, 0.1, 0.0) == 0
+    assert L.lib.fruid_density_step_dev_batch(arr(a, b), 0, sim._h, 0.1, 0.0) == 0
+    assert L.lib.fruid_density_step_dev_batch(arr(a, a), 2, sim._h, 0.1, 0.0) == L.ERR_BAD_ARG
+    assert L.lib.fruid_density_step_dev_batch(arr(a, c), 2, sim._h, 0.1, 0.0) == L.ERR_SIZE_MISMATCH
+    assert L.lib.fruid_density_step_dev_batch(None, 2, sim._h, 0.1, 0.0) == L.ERR_BAD_ARG
+    assert L.lib.fruid_density_step_dev_batch(arr(a, b), 2, None, 0.1, 0.0) == L.ERR_BAD_ARG
+
+
 def test_density_step_with_host_velocity(fb, oracle_mod):
     w, h = 90, 77
     rng = np.random.default_rng(12)
