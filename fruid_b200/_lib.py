@@ -88,6 +88,7 @@ SIGNATURES = {
     "fruid_density_sync": [_vp],
     "fruid_draw_density": [_vp, _vp, _vp, _vp, _f, _vp],
     "fruid_density_colors": [_vp, _vp, _vp, _vp, _vp],
+    "fruid_draw_velocity_lines": [_vp, _f, _vp],
     "fruid_op_add_source": [_vp, _vp, _sz, _sz, _f],
     "fruid_op_set_bnd": [_i, _vp, _sz, _sz],
     "fruid_op_lin_solve": [_i, _vp, _vp, _vp, _sz, _sz, _f, _f, _i, _i],

@@ -60,4 +60,33 @@ __global__ void __launch_bounds__(256) k_draw_density(const float* __restrict__ 
     }
 }
 
+// draw_velocity_lines (src/main.rs:185-216): per cell the line {tail, tip} = 2 vertices {pos[3], color[3]},
+// cell index i*h + j like draw_density.  Only +, *, /, sqrt: bit-exact against the CPU restatement.
+__global__ void __launch_bounds__(256) k_draw_velocity_lines(const float* __restrict__ u, const float* __restrict__ v, Geom g,
+                                                             float z, float cell_w, float cell_h, float* __restrict__ out) {
+    __shared__ float2 tile[32][33];
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = i0 + threadIdx.x, j = j0 + r;
+        if (i < g.w && j < g.h) tile[r][threadIdx.x] = make_float2(u[at(g, i, j)], v[at(g, i, j)]);
+    }
+    __syncthreads();
+    const float half_w = fdiv(cell_w, 2.0f), half_h = fdiv(cell_h, 2.0f);
+    const float len_num = fmul(cell_h, 2.0f);
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int i = i0 + r, j = j0 + threadIdx.x;  // j fastest across the warp
+        if (i >= g.w || j >= g.h) continue;
+        const float2 uv = tile[threadIdx.x][r];
+        const float speed = __fsqrt_rn(fadd(fmul(uv.x, uv.x), fmul(uv.y, uv.y)));                 // main.rs:197
+        const float tail_x = fadd(fsub(fmul(fdiv((float)i, (float)g.w), 2.0f), 1.0f), half_w);   // main.rs:190,206
+        const float tail_y = fadd(fsub(fmul(fdiv((float)j, (float)g.h), 2.0f), 1.0f), half_h);   // main.rs:192,207
+        const float len = fdiv(len_num, speed);                                                   // main.rs:210
+        const float tip_x = fadd(tail_x, fmul(uv.x, len)), tip_y = fadd(tail_y, fmul(uv.y, len));
+        float4* o = reinterpret_cast<float4*>(out + ((size_t)i * g.h + j) * 12);
+        o[0] = make_float4(tail_x, tail_y, z, speed);
+        o[1] = make_float4(speed, speed, tip_x, tip_y);
+        o[2] = make_float4(z, speed, speed, speed);
+    }
+}
+
 }  // namespace fruid

@@ -1147,6 +1147,24 @@ extern "C" int fruid_density_colors(fruid_density_t* c, fruid_density_t* m, frui
     return draw_density_impl(c, m, y, k, 0.0f, host_rgb, false);
 }
 
+// draw_velocity_lines (src/main.rs:185-216) of sim.uv(): 12 floats per cell {tail, tip} x {pos[3], color[3]}.
+extern "C" int fruid_draw_velocity_lines(fruid_fluid_t* f, float z, float* host_vertices) {
+    NEED(f);
+    if (!host_vertices) return fail(FRUID_ERR_BAD_ARG, "null host pointer");
+    FieldSet& S = f->s;
+    if (S.is_slab()) return fail(FRUID_ERR_BAD_ARG, "draw_velocity_lines needs a whole single-GPU field");
+    const size_t bytes = (size_t)S.g.w * S.g.h * 12 * sizeof(float);
+    float* dev = nullptr;
+    CU(cudaMallocAsync(&dev, bytes, S.stream));
+    const dim3 grid((S.g.w + 31) / 32, (S.g.h + 31) / 32), block(32, 8);
+    const float cw = 2.0f / (float)S.g.w, ch = 2.0f / (float)S.g.h;  // main.rs:186-187
+    LAUNCH("k_draw_velocity_lines", S.stream, (k_draw_velocity_lines<<<grid, block, 0, S.stream>>>(S.buf[0], S.buf[1], S.g, z, cw, ch, dev)));
+    CU(cudaMemcpyAsync(host_vertices, dev, bytes, cudaMemcpyDeviceToHost, S.stream));
+    CU(cudaFreeAsync(dev, S.stream));
+    CU(cudaStreamSynchronize(S.stream));
+    return 0;
+}
+
 // Page-lock caller-owned host arrays (the Vec<f32> inside an Array2D has a fixed length for
 // the object's life) so uploads/downloads run at full PCIe rate.
 // Tile shape of the fused Jacobi kernel: R rows per warp x NW warps (tile = 128 x R*NW cells).

@@ -599,19 +599,48 @@ static inline int jacobi_tile_max_T(int R, int NW) {
     return H & ~1;
 }
 
+static inline long jacobi_tile_count(const Geom& g, int R, int NW, int T) {
+    const int H = T + (T & 1), TH = R * NW;
+    return (long)tiles_needed(g.w, 128, 128 - 2 * H) * tiles_needed(g.h, TH, TH - 2 * H);
+}
+
+// Tile shape and fused depth per launch.  The kernel's cost per tile and sweep is proportional to the
+// tile's rows (it is issue bound), so as long as a tiling leaves SMs idle a SMALLER tile finishes sooner.
+// Measured scene step (tools/small_grid_cfg_probe.py, us; 128x128 tiles at T = 20 in brackets):
+//   250^2: 86 with 128x32 tiles (162)    512^2: 104 with 128x48 (167)
+//   768^2: 119 with 128x64 (169)         1024^2: 156 with 128x96 (175)       all at T = 10.
+// From ~1200^2 upwards every SM has a tile anyway and the least halo recompute wins: 128x128, T = 10.
+// Automatic choice (until fruid_set_tile_config pins a shape; always the pinned / default shape in slab mode,
+// whose halo bookkeeping assumes it): the first of these that gives every tile its own SM.
+static bool g_tile_auto = true;
+struct TilePlan { int R, NW, T; };
+static const TilePlan kSmallGridPlans[] = {{2, 16, 10}, {3, 16, 10}, {2, 32, 10}, {4, 24, 10}, {8, 16, 20}};
+
 static inline int jacobi_tile_default_fused(const Geom& g, int iters) {
     int T = g_tile_default_T;
-    const int R = g_tile_cfg.R, NW = g_tile_cfg.NW, TH = R * NW;
-    const int mx = jacobi_tile_max_T(R, NW);
-    // Small grids are launch-latency bound and leave most SMs idle anyway: when the tiling at the
-    // default depth cannot even give every SM one tile, fuse a whole 20-sweep solve per launch
-    // (more halo recompute on SMs that would otherwise idle, half the launches).
-    const int H = T + (T & 1);
-    const long tiles = (long)tiles_needed(g.w, 128, 128 - 2 * H) * tiles_needed(g.h, TH, TH - 2 * H);
-    if (tiles < 148 && g.gh == g.h) T = 20;
+    const bool whole = (g.gh == g.h);
+    if (whole && g_tile_auto) {
+        for (const TilePlan& p : kSmallGridPlans) {
+            const int t = p.T > iters ? iters : p.T;
+            if (jacobi_tile_count(g, p.R, p.NW, t) <= 148) return t < 1 ? 1 : t;
+        }
+    } else if (whole) {
+        // pinned shape: when the tiling at the default depth cannot even give every SM one tile, fuse a
+        // whole 20-sweep solve per launch (more halo recompute on SMs that would otherwise idle, half the launches)
+        if (jacobi_tile_count(g, g_tile_cfg.R, g_tile_cfg.NW, T) < 148) T = 20;
+    }
+    const int mx = jacobi_tile_max_T(g_tile_cfg.R, g_tile_cfg.NW);
     if (T > mx) T = mx;
     if (T > iters) T = iters;
     return T < 1 ? 1 : T;
+}
+
+// Shape for a launch of T fused sweeps.
+static inline TileCfg jacobi_tile_shape(const Geom& g, int T) {
+    if (g_tile_auto && g.gh == g.h)
+        for (const TilePlan& p : kSmallGridPlans)
+            if (T <= jacobi_tile_max_T(p.R, p.NW) && jacobi_tile_count(g, p.R, p.NW, T) <= 148) return TileCfg{p.R, p.NW};
+    return g_tile_cfg;
 }
 
 template <int R, int NW, int MODE>
@@ -644,13 +673,15 @@ static int jacobi_tile_launch_cfg(const TileArgs& A, int mode, cudaStream_t st) 
     return jacobi_tile_launch_mode<R, NW, MODE_ONE>(A, st);
 }
 
-#define FRUID_TILE_CONFIGS(X) X(8, 16) X(10, 16) X(6, 16) X(6, 20) X(7, 20) X(5, 24) X(4, 24) X(8, 12) X(4, 16)
+#define FRUID_TILE_CONFIGS(X) X(8, 16) X(10, 16) X(6, 16) X(6, 20) X(7, 20) X(5, 24) X(4, 24) X(8, 12) X(4, 16) X(2, 32) X(2, 16) X(4, 8) X(3, 16)
 
 // Returns 0 or a negative fruid_status (-7 = bad argument, -4 = CUDA error).
 static int jacobi_tile_launch(float* out, const float* x, const float* x0, const Geom& g, float a, float c, int b, int T,
                               int x_is_zero, cudaStream_t st, int fuse_src = 0, float src_dt = 0.f, float* z_out = nullptr) {
-    const int R = g_tile_cfg.R, NW = g_tile_cfg.NW, TH = R * NW;
-    if (T < 1 || T > jacobi_tile_max_T(R, NW)) return -7;
+    if (T < 1) return -7;
+    const TileCfg cfg = jacobi_tile_shape(g, T);
+    const int R = cfg.R, NW = cfg.NW, TH = R * NW;
+    if (T > jacobi_tile_max_T(R, NW)) return -7;
     TileArgs A;
     if (int r = tile_tensor_map(x0, g.pitch, g.h, TH, &A.tm_x0)) return r;
     if (int r = tile_tensor_map(x, g.pitch, g.h, TH, &A.tm_x)) return r;
@@ -694,7 +725,11 @@ static int jacobi_tile_launch(float* out, const float* x, const float* x0, const
 }
 
 static inline int jacobi_tile_set_cfg(int R, int NW, int T) {
-#define FRUID_TILE_OK(r, nw) if (R == r && NW == nw) { g_tile_cfg = {R, NW}; if (T > 0) g_tile_default_T = T; return 0; }
+    if (R == 0 && NW == 0) {  // back to the automatic choice
+        g_tile_auto = true; g_tile_cfg = {8, 16}; g_tile_default_T = T > 0 ? T : 10;
+        return 0;
+    }
+#define FRUID_TILE_OK(r, nw) if (R == r && NW == nw) { g_tile_cfg = {R, NW}; g_tile_auto = false; if (T > 0) g_tile_default_T = T; return 0; }
     FRUID_TILE_CONFIGS(FRUID_TILE_OK)
 #undef FRUID_TILE_OK
     return -7;

@@ -25,6 +25,15 @@ def density_colors(c, m, y, k) -> np.ndarray:
     return out
 
 
+def draw_velocity_lines(sim, z: float = 0.5) -> np.ndarray:
+    """Vertex buffer of draw_velocity_lines(sim.uv(), z) (main.rs:185-216): array (w*h*2, 6),
+    {tail, tip} per cell in the reference's push order."""
+    w, h = sim.width(), sim.height()
+    out = np.empty((w * h * 2, 6), np.float32)
+    check(lib.fruid_draw_velocity_lines(sim._h, z, ptr(out)))
+    return out
+
+
 def write_ppm(path: str, rgb: np.ndarray) -> None:
     """Binary PPM (P6) of an (h, w, 3) float image; colours are clamped to [0, 1] like a framebuffer."""
     img = np.nan_to_num(np.asarray(rgb, np.float32), nan=0.0, posinf=1.0, neginf=0.0)

@@ -67,7 +67,10 @@ uint64_t fruid_kernel_launch_count(void);
 const char *fruid_build_info(void);
 
 /* Tuning knob: tile shape of the fused Jacobi kernel (rows per warp x warps per CTA; the tile
- * is 128 x rows_per_warp*warps cells) and the default number of fused sweeps (0 = keep). */
+ * is 128 x rows_per_warp*warps cells) and the default number of fused sweeps (0 = keep).
+ * By default the library chooses per launch: 128x128 tiles and 10 sweeps per launch, smaller tiles
+ * (128x64, 128x96) and up to 20 sweeps on grids too small to give every SM a tile.  A call pins the
+ * shape for every later launch; (0, 0, T) returns to the automatic choice.  Results never change. */
 int fruid_set_tile_config(int rows_per_warp, int warps, int default_fused);
 
 /* Tuning knob: replay FluidSim::step / DensitySim::step as captured CUDA graphs (default 1). */
@@ -148,6 +151,10 @@ int fruid_draw_density(fruid_density_t *c, fruid_density_t *m, fruid_density_t *
                        float *host_vertices);
 int fruid_density_colors(fruid_density_t *c, fruid_density_t *m, fruid_density_t *y, fruid_density_t *k,
                          float *host_rgb);
+/* draw_velocity_lines(sim.uv(), z), src/main.rs:185-216 (the reference calls it once at
+ * init, main.rs:56): per cell, i outer / j inner, the line {tail, tip} as two vertices {pos[3], color[3]}
+ * -- host_vertices holds w*h*12 floats.  Bit-exact (+, *, /, sqrt only). */
+int fruid_draw_velocity_lines(fruid_fluid_t *f, float z, float *host_vertices);
 
 /* ---- Multi-GPU y-slabs: one process per GPU -----------------------------------
  * Rank `rank` of `world` (<= 8) owns global rows [y0, y1) of the w x gh field plus 22 halo rows

@@ -55,6 +55,8 @@ def _bind(lib):
     lib.fruid_oracle_vel_step.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p, _sz, _sz, _f, _f, _i, _i]
     lib.fruid_oracle_draw_density.argtypes = [_f32p, _f32p, _f32p, _f32p, _sz, _sz, _f, _f32p]
     lib.fruid_oracle_draw_density.restype = None
+    lib.fruid_oracle_draw_velocity_lines.argtypes = [_f32p, _f32p, _sz, _sz, _f, _f32p]
+    lib.fruid_oracle_draw_velocity_lines.restype = None
     lib.fruid_oracle_has_openmp.restype = _i
     for name in ("add_source", "set_bnd", "lin_solve", "diffuse", "advect", "diff_acc", "project",
                  "dens_step", "vel_step"):

@@ -276,3 +276,36 @@ void fruid_oracle_draw_density(const float *c, const float *m, const float *y, c
         }
     }
 }
+
+/* ---- "next" row f-4: draw_velocity_lines, src/main.rs:185-216 (init-only debug
+ * visualisation, main.rs:56).  Per cell (i outer, j inner) two vertices {pos[3], color[3]}: the
+ * tail at the cell centre and the tip at tail + (u, v) * (2*cell_height / speed), both coloured
+ * [speed; 3].  `verts` holds w*h*2*6 floats in push order.  `x.powf(2.)` is restated as x*x (LLVM
+ * folds pow(x, 2.0) into a multiply; the values agree for every input either way up to libm's
+ * rounding of powf).  speed == 0 gives len = inf and a NaN tip (0*inf), as in the reference. */
+void fruid_oracle_draw_velocity_lines(const float *u, const float *v, size_t w, size_t h, float z, float *verts) {
+    float cell_width = 2.0f / (float)w;
+    float cell_height = 2.0f / (float)h;
+    size_t n = 0;
+    for (size_t i = 0; i < w; ++i) {
+        float i_frac = ((float)i / (float)w) * 2.0f - 1.0f;
+        for (size_t j = 0; j < h; ++j) {
+            float j_frac = ((float)j / (float)h) * 2.0f - 1.0f;
+            float uu = u[IDX(i, j, w)];
+            float vv = v[IDX(i, j, w)];
+            float speed = sqrtf(uu * uu + vv * vv);
+            float tail_x = i_frac + cell_width / 2.0f;
+            float tail_y = j_frac + cell_height / 2.0f;
+            float len = cell_height * 2.0f / speed;
+            float pos[2][2] = {{tail_x, tail_y}, {tail_x + uu * len, tail_y + vv * len}};
+            for (int q = 0; q < 2; ++q) {
+                verts[n++] = pos[q][0];
+                verts[n++] = pos[q][1];
+                verts[n++] = z;
+                verts[n++] = speed;
+                verts[n++] = speed;
+                verts[n++] = speed;
+            }
+        }
+    }
+}

@@ -224,6 +224,28 @@ def test_draw_density_known_answers(oracle_mod):
     assert np.allclose(v[..., 4], np.log2(1 / 3.0 + 2), rtol=1e-6)
 
 
+def test_draw_velocity_lines_known_answers(oracle_mod):
+    """main.rs:185-216: the tail sits at the cell centre, the tip at tail + (u, v) * 2*cell_height/speed
+    (so every line is 2 cell heights long), colour = speed; zero velocity gives a NaN tip (0 * inf)."""
+    w, h = 8, 4
+    u = np.zeros((h, w), np.float32)
+    v = np.zeros((h, w), np.float32)
+    u[1, 2], v[1, 2] = 3.0, 4.0    # cell (i=2, j=1): speed 5
+    u[3, 5] = -2.0                 # cell (i=5, j=3): speed 2, pointing to -x
+    out = np.zeros(w * h * 12, np.float32)
+    oracle_mod.lib().fruid_oracle_draw_velocity_lines(u, v, w, h, 0.75, out)
+    out = out.reshape(w, h, 2, 6)
+    assert np.all(out[..., 2] == 0.75)
+    tail, tip = out[2, 1, 0], out[2, 1, 1]
+    assert tail[0] == np.float32(2 / 8 * 2 - 1 + 1 / 8) and tail[1] == np.float32(1 / 4 * 2 - 1 + 1 / 4)
+    assert np.all(tail[3:] == 5.0) and np.all(tip[3:] == 5.0)
+    ln = np.float32(0.5) * np.float32(2) / np.float32(5)
+    assert tip[0] == tail[0] + np.float32(3) * ln and tip[1] == tail[1] + np.float32(4) * ln
+    tail, tip = out[5, 3, 0], out[5, 3, 1]
+    assert tip[0] == tail[0] - np.float32(1.0) and tip[1] == tail[1]      # 2 * (2*0.5/2) = 1 to the left
+    assert np.all(out[0, 0, :, 3:] == 0.0) and np.isnan(out[0, 0, 1, :2]).all() and not np.isnan(out[0, 0, 0]).any()
+
+
 @pytest.mark.parametrize("w,h,visc", [(7, 6, 0.0), (6, 9, 2e-3), (3, 3, 1e-3)])
 def test_oracle_matches_literal_transliteration(oracle_mod, w, h, visc):
     """tests/ref_literal.py is a statement-by-statement Python transliteration of src/lib.rs (same names,

@@ -473,13 +473,41 @@ def test_full_size_fused_depth_and_tile_shape_do_not_change_results(fb):
     ref = _run_handles(fb, n, sc, 1, 1e-6, fused=1)
     L = fb._lib.lib
     try:
-        for (r, nw, t) in ((8, 16, 10), (8, 16, 4), (8, 16, 20), (4, 16, 6), (6, 20, 10)):
+        for (r, nw, t) in ((8, 16, 10), (8, 16, 4), (8, 16, 20), (4, 16, 6), (6, 20, 10), (2, 32, 10), (3, 16, 20),
+                           (2, 16, 6), (4, 8, 10), (4, 24, 20)):
             fb._lib.check(L.fruid_set_tile_config(r, nw, 0))
             got = _run_handles(fb, n, sc, 1, 1e-6, fused=t)
             for g, want, name in zip(got, ref, NAMES6):
                 assert_bits(g, want, f"{name} (tile {r}x{nw}, T={t})")
     finally:
-        fb._lib.check(L.fruid_set_tile_config(8, 16, 0))
+        fb._lib.check(L.fruid_set_tile_config(0, 0, 10))  # back to the automatic choice
+
+
+@pytest.mark.parametrize("n", [250, 400, 640, 1024, 1300, 1700])
+@pytest.mark.parametrize("visc", [0.0, 1e-5])
+def test_automatic_tile_shape_on_small_grids(fb, oracle_mod, n, visc):
+    """The library picks smaller tiles / deeper fusion on grids that cannot give every SM a 128x128 tile
+    (250..1024), the default shape above: same bits as the pinned default shape, and as the oracle."""
+    import bench
+    sc = bench.make_scene(n, n)
+    L = fb._lib.lib
+    auto = _run_handles(fb, n, sc, 3, visc)          # 3 steps: direct, captured, replayed
+    try:
+        fb._lib.check(L.fruid_set_tile_config(8, 16, 10))
+        pinned = _run_handles(fb, n, sc, 3, visc)
+    finally:
+        fb._lib.check(L.fruid_set_tile_config(0, 0, 10))
+    for g, want, name in zip(auto, pinned, NAMES6):
+        assert_bits(g, want, f"{name} (automatic vs pinned 8x16)")
+    if visc == 0.0:
+        of, od = oracle_mod.Fluid(n, n), oracle_mod.Density(n, n)
+        of.u[:], of.v[:], of.u_prev[:], of.v_prev[:] = sc["u"], sc["v"], sc["u_prev"], sc["v_prev"]
+        od.dens[:], od.dens_prev[:] = sc["dens"], sc["dens_prev"]
+        for _ in range(3):
+            of.step(0.01, visc)
+            od.step((of.u, of.v), 0.01, visc)
+        for g, want, name in zip(auto, (of.u, of.v, of.u_prev, of.v_prev, od.dens, od.dens_prev), NAMES6):
+            assert_bits(g, want, name)
 
 
 @pytest.mark.parametrize("iters", [40, 100, 200, 500])
@@ -602,6 +630,35 @@ def test_draw_density_matches_reference_viewer(fb, oracle_mod, w, h, tmp_path):
     assert np.array_equal(rgb, got[::4, 3:].reshape(w, h, 3).transpose(1, 0, 2))
     fb.render.write_ppm(str(tmp_path / "frame.ppm"), rgb)
     assert (tmp_path / "frame.ppm").stat().st_size == len(b"P6\n%d %d\n255\n" % (w, h)) + w * h * 3
+
+
+@pytest.mark.parametrize("w,h", [(250, 250), (33, 70), (2, 2), (129, 31)])
+def test_draw_velocity_lines_matches_reference_viewer(fb, oracle_mod, w, h):
+    """draw_velocity_lines (main.rs:185-216) after a step of an injected flow (main.rs:48,56), plus
+    special values (zero velocity -> NaN tip, inf, NaN, denormals): bit-exact."""
+    rng = np.random.default_rng(w * 3 + h)
+    u, v = rand_field(rng, w, h, 30.0), rand_field(rng, w, h, 30.0)
+    u.flat[::7] = 0.0
+    v.flat[::7] = 0.0
+    sp = np.array([np.inf, -np.inf, np.nan, 1e-42, -0.0, 3e38, 1e-20], np.float32)
+    u.flat[1:1 + min(len(sp), u.size - 1)] = sp[:u.size - 1]
+    v.flat[2:2 + min(len(sp), v.size - 2)] = sp[:v.size - 2]
+    sim = fb.FluidSim(w, h)
+    fb._lib.check(fb._lib.lib.fruid_fluid_upload(sim._h, 0, fb._lib.ptr(u)))
+    fb._lib.check(fb._lib.lib.fruid_fluid_upload(sim._h, 1, fb._lib.ptr(v)))
+    got = fb.render.draw_velocity_lines(sim, z=0.5)
+    want = np.zeros(w * h * 12, np.float32)
+    oracle_mod.lib().fruid_oracle_draw_velocity_lines(u, v, w, h, 0.5, want)
+    assert_bits(got, want.reshape(-1, 6), "velocity lines")
+    if w > 4 and h > 4:  # ... and of a stepped simulation, as the viewer calls it
+        sim2, o2 = fb.FluidSim(w, h), oracle_mod.Fluid(w, h)
+        sim2.uv_mut()[0][(w // 2, h // 2)] = -4500.0
+        o2.u_prev[h // 2, w // 2] = -4500.0
+        sim2.step(0.1, 0.0)
+        o2.step(0.1, 0.0)
+        got = fb.render.draw_velocity_lines(sim2, z=0.0)
+        oracle_mod.lib().fruid_oracle_draw_velocity_lines(o2.u, o2.v, w, h, 0.0, want)
+        assert_bits(got, want.reshape(-1, 6), "velocity lines after a step")
 
 
 @pytest.mark.parametrize("c", [1.6704, 3.924, 1.0000001, 7.3e-3, 513.77, 1.9999999])
