@@ -6,6 +6,7 @@
 // contracts or reorders; the library is additionally built with -fmad=false and
 // without --use_fast_math (default -prec-div=true -ftz=false).
 #pragma once
+#include <utility>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -78,6 +79,29 @@ __device__ __forceinline__ void store_with_bnd(float* __restrict__ out, const Ge
 // mix(), src/lib.rs:80-82: (1 - t)*a + t*b, unfused.
 __device__ __forceinline__ float mixf(float a, float b, float t) {
     return fadd(fmul(fsub(1.0f, t), a), fmul(t, b));
+}
+
+// Programmatic dependent launch: a kernel launched through launch_pdl() may be scheduled while its
+// predecessor in the stream is still running, which hides the ~3 us launch latency between the dependent
+// kernels of a step (small grids are bound by exactly that).  Every such kernel starts with pdl_enter():
+// wait until the predecessor has completed and its writes are visible (nothing is read or written before),
+// then allow the successor to be scheduled.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+static bool g_pdl_enabled = true;
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl && g_pdl_enabled) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 }  // namespace fruid

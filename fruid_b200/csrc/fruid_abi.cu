@@ -139,7 +139,7 @@ static inline dim3 vec_grid(const Geom& g) { return dim3(((g.w + 3) / 4 + 31) / 
 static int op_add_source(float* x1, const float* s1, float* x2, const float* s2, const Geom& g, float dt,
                          cudaStream_t st) {
     const size_t n4 = g.pitch * (size_t)g.h / 4;
-    LAUNCH("k_add_source4", st, k_add_source4<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x1, s1, x2, s2, n4, dt));
+    LAUNCH("k_add_source4", st, launch_pdl(true, k_add_source4, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, x1, s1, x2, s2, n4, dt));
     return 0;
 }
 
@@ -264,7 +264,7 @@ static int op_advect(int nf, float* const* d, const float* const* d0, const int*
     SlabTable T = *tab;
     T.grid_x = (int)grid1.x;
 #define FRUID_ADVECT(NF, PASS, name) \
-    LAUNCH(name, st, (k_advect4<NF, PASS><<<(PASS == 2 ? dim3(296) : grid1), vec_block(), 0, st>>>(a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, T)))
+    LAUNCH(name, st, launch_pdl(PASS != 2, k_advect4<NF, PASS>, (PASS == 2 ? dim3(296) : grid1), vec_block(), 0, st, a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, T))
     if (nf < 1 || nf > ADVECT_MAX_FIELDS || (multi && nf > 2)) return fail(FRUID_ERR_BAD_ARG, "advect: unsupported field count %d", nf);
     if (!multi) {
         switch (nf) {
@@ -293,10 +293,10 @@ static int op_project(float* u, float* v, float*& p, float* div, float*& scratch
     // the fused solver the zero field is not materialised, the first block is told instead.
     const bool p_implicit_zero = resolve_fused(g, iters, fused) > 1;
     LAUNCH("k_divergence4", st,
-           k_divergence4<<<vec_grid(g), vec_block(), 0, st>>>(div, p_implicit_zero ? nullptr : p, u, v, g, sx, sy));
+           launch_pdl(true, k_divergence4, vec_grid(g), vec_block(), 0, st, div, p_implicit_zero ? nullptr : p, u, v, g, sx, sy));
     TRY(op_lin_solve(B_POSITIVE, p, div, scratch, g, 1.0f, 4.0f, iters, fused, st, p_implicit_zero));  // lib.rs:162
     const float gx = -0.5f * (float)g.nx, gy = -0.5f * (float)g.ny;  // lib.rs:164-165
-    LAUNCH("k_gradient4", st, k_gradient4<<<vec_grid(g), vec_block(), 0, st>>>(u, v, p, g, gx, gy));
+    LAUNCH("k_gradient4", st, launch_pdl(true, k_gradient4, vec_grid(g), vec_block(), 0, st, u, v, p, g, gx, gy));
     return 0;
 }
 
@@ -720,11 +720,11 @@ static int project_slab(FieldSet& S, float*& u, float*& v, float*& p, float*& di
     const Geom& g = S.g;
     cudaStream_t st = S.stream;
     const float sx = -0.5f / (float)g.nx, sy = -0.5f / (float)g.ny;
-    LAUNCH("k_divergence4", st, (k_divergence4<<<vec_grid(g), vec_block(), 0, st>>>(div, nullptr, u, v, g, sx, sy)));  // m: HALO -> HALO-1
+    LAUNCH("k_divergence4", st, launch_pdl(true, k_divergence4, vec_grid(g), vec_block(), 0, st, div, (float*)nullptr, u, v, g, sx, sy));  // m: HALO -> HALO-1
     SlabSolve ss{SLAB_HALO, SLAB_HALO - 1, 1, [&S](std::initializer_list<float*> f) { return S.exchange(f); }};
     TRY(op_lin_solve(B_POSITIVE, p, div, S.buf[4], g, 1.0f, 4.0f, S.iters, T, st, true, false, 0.f, nullptr, &ss));
     const float gx = -0.5f * (float)g.nx, gy = -0.5f * (float)g.ny;
-    LAUNCH("k_gradient4", st, (k_gradient4<<<vec_grid(g), vec_block(), 0, st>>>(u, v, p, g, gx, gy)));  // needs p one row out
+    LAUNCH("k_gradient4", st, launch_pdl(true, k_gradient4, vec_grid(g), vec_block(), 0, st, u, v, p, g, gx, gy));  // needs p one row out
     return 0;
 }
 
@@ -849,6 +849,9 @@ static int run_step_graphed(FieldSet& S, float dt, float p, const void* a0, cons
     return run_graphed(S.graph, S, {&S}, dt, p, a0, a1, {}, body);
 }
 // Tuning / debugging knob: replay steps as CUDA graphs (default on).
+// Tuning / debugging knob: programmatic dependent launch between the kernels of a step (default on).
+namespace { struct PdlEnv { PdlEnv() { if (const char* e = getenv("FRUID_B200_LAUNCH_OVERLAP")) g_pdl_enabled = atoi(e) != 0; } } g_pdl_env; }
+extern "C" int fruid_set_launch_overlap(int on) { g_pdl_enabled = on != 0; g_cfg_epoch.fetch_add(1); return 0; }
 extern "C" int fruid_set_graphs_enabled(int on) { g_graphs_enabled = on != 0; g_cfg_epoch.fetch_add(1); return 0; }
 
 #define NEED(h) do { if (!(h)) return fail(FRUID_ERR_BAD_ARG, "null handle"); CU(cudaSetDevice((h)->s.device)); } while (0)

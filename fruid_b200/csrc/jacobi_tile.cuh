@@ -380,6 +380,7 @@ constexpr size_t jacobi_tile_smem_bytes() {
 
 template <int R, int NW, int MODE>
 __global__ void __launch_bounds__(NW * 32, 1) k_jacobi_tile(const __grid_constant__ TileArgs A) {
+    pdl_enter();
     constexpr int TH = R * NW;
     constexpr uint32_t TILE_BYTES = TH * 512;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -660,8 +661,7 @@ static int jacobi_tile_launch_mode(const TileArgs& A, cudaStream_t st) {
     }
     const int ntiles = A.ntx * A.nty;
     dim3 grid(ntiles < num_sms ? ntiles : num_sms), block(NW * 32);
-    k_jacobi_tile<R, NW, MODE><<<grid, block, smem, st>>>(A);
-    return 0;
+    return launch_pdl(true, k_jacobi_tile<R, NW, MODE>, grid, block, smem, st, A) == cudaSuccess ? 0 : -4;
 }
 
 template <int R, int NW>

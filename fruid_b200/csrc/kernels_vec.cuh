@@ -69,6 +69,7 @@ __device__ __forceinline__ void store_row4_bnd(float* __restrict__ out, const Ge
 // add_source over all cells (src/lib.rs:5-10), two fields per launch; rows as float4.
 __global__ void k_add_source4(float* __restrict__ x1, const float* __restrict__ s1, float* __restrict__ x2,
                               const float* __restrict__ s2, size_t n4, float dt) {
+    pdl_enter();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     float4* X1 = reinterpret_cast<float4*>(x1);
@@ -92,6 +93,7 @@ __device__ __forceinline__ void edge_vals(const float* __restrict__ f, const Geo
 // is then told that its initial iterate is identically zero).
 __global__ void k_divergence4(float* __restrict__ div, float* __restrict__ p, const float* __restrict__ u,
                               const float* __restrict__ v, Geom g, float sx, float sy) {
+    pdl_enter();
     const int gx0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
     const int gy = blockIdx.y * blockDim.y + threadIdx.y + 1;  // LOCAL row; needs rows gy-1, gy+1
     if (gx0 >= g.w || gy > g.h - 2) return;
@@ -112,6 +114,7 @@ __global__ void k_divergence4(float* __restrict__ div, float* __restrict__ p, co
 // set_bnd(NegX,u); set_bnd(NegY,v).  In place; each thread touches only its own cells.
 __global__ void k_gradient4(float* __restrict__ u, float* __restrict__ v, const float* __restrict__ p, Geom g, float gxs,
                             float gys) {
+    pdl_enter();
     const int gx0 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
     const int gy = blockIdx.y * blockDim.y + threadIdx.y + 1;  // LOCAL row; needs rows gy-1, gy+1
     if (gx0 >= g.w || gy > g.h - 2) return;
@@ -249,6 +252,7 @@ __device__ __forceinline__ void advect4_block(const AdvectArgs& a, const float* 
 template <int NF, int PASS>
 __global__ void k_advect4(AdvectArgs a, const float* __restrict__ u, const float* __restrict__ v, Geom g, float dt0,
                           float dt1, float xmax, float ymax, int ly0, int ly1, const __grid_constant__ SlabTable tab) {
+    pdl_enter();
     if (PASS != 2) {
         // Folded "src_done" broadcast: the kernels that wrote the gathered fields precede this launch in
         // stream order, so they are final; tell every rank (nobody waits here).

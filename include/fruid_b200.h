@@ -75,6 +75,10 @@ int fruid_set_tile_config(int rows_per_warp, int warps, int default_fused);
 
 /* Tuning knob: replay FluidSim::step / DensitySim::step as captured CUDA graphs (default 1). */
 int fruid_set_graphs_enabled(int on);
+/* Tuning knob: let the dependent kernels of a step be scheduled while their predecessor is still running
+ * (programmatic dependent launch; each kernel first waits for the predecessor's completion, so results
+ * cannot change).  Default on (environment FRUID_B200_LAUNCH_OVERLAP=0 turns it off at load). */
+int fruid_set_launch_overlap(int on);
 
 /* Page-lock / unlock a caller-owned host array (e.g. the Vec<f32> inside an Array2D). */
 int fruid_host_register(void *p, size_t bytes);

@@ -5,6 +5,9 @@ import bench, fruid_b200 as fb
 from fruid_b200 import _lib
 L = _lib.lib
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+if len(sys.argv) > 2:
+    L.fruid_set_launch_overlap(int(sys.argv[2]))
+    print("launch overlap (PDL):", int(sys.argv[2]))
 sc = bench.make_scene(n, n)
 def setup():
     sim, den = fb.FluidSim(n, n), fb.DensitySim(n, n)
