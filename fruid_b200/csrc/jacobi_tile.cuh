@@ -36,8 +36,11 @@
 // by a constant with an FMA, Brisebarre-Muller-Raina 2004) -- for "almost all" c; the claim is not
 // taken on trust: before a value of c is used, a kernel compares q with __fdiv_rn(v, c) for ALL 2^23
 // significands of v (results scale exactly with the exponent while nothing under/overflows), and
-// falls back to MODE_GENERAL if a single one differs.  Inputs outside [2^-60, 2^60) (zeros,
-// denormals, huge values, inf, NaN) take __fdiv_rn per element.
+// tries MODE_RECIP3 if a single one differs (it does for about one divisor in a few hundred -- among them
+// c = 1 + 4*(0.01*1e-6*4094*4094), the viscous 4096^2 bench case): q0 = v*zh, r = fma(-q0, c, v) (the exact
+// residual), q = fma(r, zh, q0), Markstein's correction step, one instruction more; verified the same way,
+// and only if that fails too MODE_GENERAL is used.  Inputs outside [2^-60, 2^60) (zeros, denormals, huge
+// values, inf, NaN) take __fdiv_rn per element.
 #pragma once
 #include <cuda.h>
 
@@ -50,7 +53,7 @@
 
 namespace fruid {
 
-enum : int { MODE_GENERAL = 0, MODE_POW2 = 1, MODE_ONE = 2, MODE_POISSON = 3, MODE_RECIP = 4 };
+enum : int { MODE_GENERAL = 0, MODE_POW2 = 1, MODE_ONE = 2, MODE_POISSON = 3, MODE_RECIP = 4, MODE_RECIP3 = 5 };
 
 struct TileArgs {
     CUtensorMap tm_x0;  // 2-D map over x0: dims (pitch, h) f32, box (128, R*NW), zero OOB fill
@@ -118,10 +121,17 @@ __device__ __forceinline__ float4 jac_row(const float4 z, float t0, float t1, fl
     s01 = __fadd2_rn(make_float2(z.x, z.y), s01);
     s23 = __fadd2_rn(make_float2(z.z, z.w), s23);
     if (MODE == MODE_GENERAL) return make_float4(fdiv(s01.x, c), fdiv(s01.y, c), fdiv(s23.x, c), fdiv(s23.y, c));
-    if (MODE == MODE_RECIP) {
-        // an FMA used as an exact-arithmetic building block of the division, not a contraction
-        const float2 q01 = __ffma2_rn(s01, make_float2(zh, zh), __fmul2_rn(s01, make_float2(zl, zl)));
-        const float2 q23 = __ffma2_rn(s23, make_float2(zh, zh), __fmul2_rn(s23, make_float2(zl, zl)));
+    if (MODE == MODE_RECIP || MODE == MODE_RECIP3) {
+        // FMAs used as exact-arithmetic building blocks of the division, not contractions
+        float2 q01, q23;
+        if (MODE == MODE_RECIP) {
+            q01 = __ffma2_rn(s01, make_float2(zh, zh), __fmul2_rn(s01, make_float2(zl, zl)));
+            q23 = __ffma2_rn(s23, make_float2(zh, zh), __fmul2_rn(s23, make_float2(zl, zl)));
+        } else {  // q0 = v*zh;  r = v - q0*c (exact);  q = q0 + r*zh
+            const float2 p01 = __fmul2_rn(s01, make_float2(zh, zh)), p23 = __fmul2_rn(s23, make_float2(zh, zh));
+            q01 = __ffma2_rn(__ffma2_rn(p01, make_float2(-c, -c), s01), make_float2(zh, zh), p01);
+            q23 = __ffma2_rn(__ffma2_rn(p23, make_float2(-c, -c), s23), make_float2(zh, zh), p23);
+        }
         const bool k0 = recip_safe(s01.x), k1 = recip_safe(s01.y), k2 = recip_safe(s23.x), k3 = recip_safe(s23.y);
         if (k0 & k1 & k2 & k3) return make_float4(q01.x, q01.y, q23.x, q23.y);
         return make_float4(k0 ? q01.x : fdiv(s01.x, c), k1 ? q01.y : fdiv(s01.y, c), k2 ? q23.x : fdiv(s23.x, c),
@@ -463,7 +473,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_jacobi_tile(const __grid_constan
 }
 
 // Exhaustive check of the MODE_RECIP division for one divisor: all 2^23 significands, two binades, both signs.
-__global__ void k_recip_verify(float c, float zh, float zl, int* bad) {
+__global__ void k_recip_verify(float c, float zh, float zl, int variant, int* bad) {
     const unsigned m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= (1u << 23)) return;
     int b = 0;
@@ -471,7 +481,13 @@ __global__ void k_recip_verify(float c, float zh, float zl, int* bad) {
     for (int k = 0; k < 4; ++k) {
         const unsigned bits = ((k & 1) ? 0x42000000u : 0x3f800000u) | ((k & 2) ? 0x80000000u : 0u) | m;
         const float v = __uint_as_float(bits);
-        const float q = __fmaf_rn(v, zh, __fmul_rn(v, zl));
+        float q;
+        if (variant == MODE_RECIP) {
+            q = __fmaf_rn(v, zh, __fmul_rn(v, zl));
+        } else {  // MODE_RECIP3
+            const float q0 = __fmul_rn(v, zh);
+            q = __fmaf_rn(__fmaf_rn(q0, -c, v), zh, q0);
+        }
         b |= (__float_as_uint(q) != __float_as_uint(__fdiv_rn(v, c)));
     }
     if (b) atomicOr(bad, 1);
@@ -479,7 +495,7 @@ __global__ void k_recip_verify(float c, float zh, float zl, int* bad) {
 
 // ---- host side -----------------------------------------------------------------------------
 // c -> (usable, zh, zl); filled by recip_for() the first time a divisor is seen (synchronises once).
-struct RecipInfo { bool ok; float zh, zl; };
+struct RecipInfo { bool ok; int mode; float zh, zl; };
 static std::mutex g_recip_mu;
 static std::unordered_map<uint32_t, RecipInfo> g_recip;
 static bool recip_for(float c, RecipInfo* out) {
@@ -488,7 +504,7 @@ static bool recip_for(float c, RecipInfo* out) {
     std::lock_guard<std::mutex> lk(g_recip_mu);
     auto it = g_recip.find(key);
     if (it != g_recip.end()) { *out = it->second; return it->second.ok; }
-    RecipInfo r{false, 0.f, 0.f};
+    RecipInfo r{false, MODE_GENERAL, 0.f, 0.f};
     int e = 0;
     (void)frexpf(c, &e);
     if (c == c && c != 0.f && e > -30 && e < 30) {  // finite, normal, moderate magnitude
@@ -498,10 +514,15 @@ static bool recip_for(float c, RecipInfo* out) {
         int* bad = nullptr;
         // never synchronise inside a stream capture: leave the divisor unverified (general path) for now
         if (cudaStreamIsCapturing(cudaStreamPerThread, &cs) == cudaSuccess && cudaMalloc(&bad, sizeof(int)) == cudaSuccess) {
-            int h = 1;
-            if (cudaMemset(bad, 0, sizeof(int)) == cudaSuccess) {
-                k_recip_verify<<<(1u << 23) / 256, 256>>>(c, r.zh, r.zl, bad);
-                if (cudaMemcpy(&h, bad, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) r.ok = (h == 0);
+            for (int variant : {(int)MODE_RECIP, (int)MODE_RECIP3}) {
+                int h = 1;
+                if (cudaMemset(bad, 0, sizeof(int)) != cudaSuccess) break;
+                k_recip_verify<<<(1u << 23) / 256, 256>>>(c, r.zh, r.zl, variant, bad);
+                if (cudaMemcpy(&h, bad, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+                if (h == 0) {
+                    r.ok = true; r.mode = variant;
+                    break;
+                }
             }
             cudaFree(bad);
         }
@@ -670,6 +691,7 @@ static int jacobi_tile_launch_cfg(const TileArgs& A, int mode, cudaStream_t st) 
     if (mode == MODE_POW2) return jacobi_tile_launch_mode<R, NW, MODE_POW2>(A, st);
     if (mode == MODE_POISSON) return jacobi_tile_launch_mode<R, NW, MODE_POISSON>(A, st);
     if (mode == MODE_RECIP) return jacobi_tile_launch_mode<R, NW, MODE_RECIP>(A, st);
+    if (mode == MODE_RECIP3) return jacobi_tile_launch_mode<R, NW, MODE_RECIP3>(A, st);
     return jacobi_tile_launch_mode<R, NW, MODE_ONE>(A, st);
 }
 
@@ -715,7 +737,7 @@ static int jacobi_tile_launch(float* out, const float* x, const float* x0, const
                 std::lock_guard<std::mutex> lk(g_recip_mu);
                 known = g_recip.count(key) != 0;
             }
-            if ((known || !capturing) && recip_for(c, &ri)) { mode = MODE_RECIP; A.zh = ri.zh; A.zl = ri.zl; }
+            if ((known || !capturing) && recip_for(c, &ri)) { mode = ri.mode; A.zh = ri.zh; A.zl = ri.zl; }
         }
     }
 #define FRUID_TILE_CASE(r, nw) if (R == r && NW == nw) return jacobi_tile_launch_cfg<r, nw>(A, mode, st);

@@ -661,7 +661,33 @@ def test_draw_velocity_lines_matches_reference_viewer(fb, oracle_mod, w, h):
         assert_bits(got, want.reshape(-1, 6), "velocity lines after a step")
 
 
-@pytest.mark.parametrize("c", [1.6704, 3.924, 1.0000001, 7.3e-3, 513.77, 1.9999999])
+def test_lin_solve_divisor_where_the_short_reciprocal_division_is_wrong(fb, O):
+    """c = 0x3fd5d0c3 (the viscous 4096^2 bench divisor): fma(v, zh, v*zl) != v/c for the significand 0x3279a9
+    (found by the library's exhaustive check, reproduced on the CPU).  With a = 0 the update is x0 / c, so fields
+    made of that significand in many binades expose a library that skipped the check."""
+    w, h = 160, 64
+    c = float(np.array([0x3fd5d0c3], np.uint32).view(np.float32)[0])
+    m = 0x3279a9
+    exps = np.arange(0x30, 0xd0, dtype=np.uint32)  # biased exponents well inside the normal range
+    vals = ((exps << 23) | m).astype(np.uint32)
+    vals = np.concatenate([vals, vals | np.uint32(0x80000000), vals + 1, vals - 1]).view(np.float32)
+    rng = np.random.default_rng(5)
+    x0 = rng.choice(vals, (h, w)).astype(np.float32)
+    x, s = rand_field(rng, w, h), np.zeros((h, w), np.float32)
+    xo, so = x.copy(), s.copy()
+    for a in (0.0, 0.25):
+        fb.ops.lin_solve(POS, x, x0, s, a, c, 2, 0)
+        O.fruid_oracle_lin_solve(POS, xo, x0, so, w, h, a, c, 2, 1)
+        assert_bits(x, xo, f"x (a={a})")
+    want = (x0[1:-1, 1:-1] / np.float32(c)).astype(np.float32)  # and the plain definition, for a = 0
+    x1, s1 = np.zeros((h, w), np.float32), np.zeros((h, w), np.float32)
+    fb.ops.lin_solve(POS, x1, x0, s1, 0.0, c, 2, 0)
+    assert_bits(x1[1:-1, 1:-1], want, "x0 / c")
+
+
+# 1.670433402061462 = 1 + 4*(0.01*1e-6*4094*4094) in f32 (0x3fd5d0c3), the viscous 4096^2 bench divisor: the two-instruction
+# reciprocal division is wrong for one significand there, so the library must pick the three-instruction form
+@pytest.mark.parametrize("c", [1.6704, 3.924, 1.0000001, 7.3e-3, 513.77, 1.9999999, 1.670433402061462])
 def test_lin_solve_general_divisor_extreme_values(fb, O, c):
     """General c takes the verified reciprocal division (MODE_RECIP) with a per-element IEEE fallback outside
     [2^-60, 2^60): feed zeros, -0, denormals, huge values, inf and NaN next to ordinary data."""
