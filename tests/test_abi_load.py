@@ -106,6 +106,22 @@ def test_sm100_native_instructions_present():
     assert "SYNCS" in sass        # mbarrier
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/fruid_b200.h must compile as C99 (plain pointers and sizes only) and a C
+    program must link against the library."""
+    import subprocess
+    src = tmp_path / "c99.c"
+    src.write_text('#include "fruid_b200.h"\n#include <stdio.h>\nint main(void) {\n'
+                   '    fruid_fluid_t *f = 0;\n    int rc = fruid_fluid_create(1, 1, &f); /* too small: an error, no CUDA call */\n'
+                   '    printf("%d %s\\n", rc, fruid_last_error());\n    return rc == FRUID_ERR_BAD_SIZE ? 0 : 1;\n}\n')
+    exe = tmp_path / "c99"
+    libdir = os.path.join(ROOT, "fruid_b200", "lib")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe),
+                    str(src), "-L", libdir, "-lfruid_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 def test_cpp_mirror_compiles_links_and_fails_loudly_without_gpu(tmp_path):
     import subprocess
     import torch
