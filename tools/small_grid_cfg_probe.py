@@ -7,9 +7,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, fruid_b200 as fb
 from fruid_b200 import _lib
 L = _lib.lib
+CFGS = [(8, 16), (4, 16), (4, 24), (2, 32), (2, 16), (4, 8), (3, 16)]
+if os.environ.get("CFGS"):  # e.g. CFGS=8x16,4x32
+    CFGS = [tuple(int(v) for v in c.split("x")) for c in os.environ["CFGS"].split(",")]
+REPS = int(os.environ.get("REPS", "200"))
 for n in [int(a) for a in sys.argv[1:]] or [250]:
     sc = bench.make_scene(n, n)
-    for (R, NW) in [(8, 16), (4, 16), (4, 24), (2, 32), (2, 16), (4, 8), (3, 16)]:
+    for (R, NW) in CFGS:
         for T in (10, 20):
             if L.fruid_set_tile_config(R, NW, 10) != 0:
                 continue
@@ -30,6 +34,6 @@ for n in [int(a) for a in sys.argv[1:]] or [250]:
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(st)
-            for _ in range(200): both()
+            for _ in range(REPS): both()
             e1.record(st); torch.cuda.synchronize()
-            print(f"n={n} R={R} NW={NW} T={T}: {e0.elapsed_time(e1) / 200 * 1e3:8.1f} us/scene step", flush=True)
+            print(f"n={n} R={R} NW={NW} T={T}: {e0.elapsed_time(e1) / REPS * 1e3:8.1f} us/scene step", flush=True)
