@@ -192,11 +192,12 @@ def run_reference(args):
 
 def workload_config(args, n_gpus):
     w = args.size
-    return {"workload": f"{w}x{w} scene step: FluidSim::step + 1x DensitySim::step, K={ITERS} sweeps per lin_solve "
+    h = args.rows if (args.rows and n_gpus == 1) else w
+    return {"workload": f"{w}x{h} scene step: FluidSim::step + 1x DensitySim::step, K={ITERS} sweeps per lin_solve "
                         f"(40 pressure sweeps/step), dt={DT}, visc={VISC}, diff={DIFF} (BASELINE.json configs[2])",
-            "grid": [w, w], "jacobi_iters": ITERS, "dyes": 1, "dt": DT, "visc": VISC, "diff": DIFF,
+            "grid": [w, h], "jacobi_iters": ITERS, "dyes": 1, "dt": DT, "visc": VISC, "diff": DIFF,
             "init": "Taylor-Green velocity at CFL~2 cells + hash noise; Gaussian dye; noisy source fields",
-            "l2": f"inputs larger than L2 (8 fields x {w * w * 4 >> 20} MiB)", "parallelism": f"slab{n_gpus}"}
+            "l2": f"inputs larger than L2 (8 fields x {w * h * 4 >> 20} MiB)", "parallelism": f"slab{n_gpus}"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -225,6 +226,8 @@ def run_b200(args):
     w = h = args.size
     if world > 1:
         return run_b200_multi(args, fb, dist, rank, world, local)
+    if args.rows:
+        h = args.rows  # a single GPU's share of a decomposed grid (the weak-scaling baseline of SURVEY.md 8d config 4)
 
     sc = make_scene(w, h)
     sim, den = fb.FluidSim(w, h), fb.DensitySim(w, h)
