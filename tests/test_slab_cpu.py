@@ -2,7 +2,7 @@
 exchange points -- restated with the CPU oracle as the per-rank operator and gloo send/recv as the
 halo exchange, must reproduce the undecomposed oracle run BIT FOR BIT on every rank's owned rows.
 
-This mirrors op_vel_step_slab / op_dens_step_slab of fruid_b200/csrc/fruid_abi.cu: exchange the
+This mirrors op_vel_step_slab / op_dens_step_slab of fruid_b200/csrc/slab_step.cuh: exchange the
 halos, run the operators on all local rows (results near a slab cut go stale one row per sweep /
 stencil application, which the 22-row halo absorbs for two blocks of 10 sweeps + divergence +
 gradient), advect from the owners' rows.  The GPU path itself is checked against the single-GPU
