@@ -23,6 +23,7 @@ struct SlabInfo {
     int attached = 1;                    // how many of them are mapped (mine counts)
     int ev_pull = 0, ev_bar = 0;         // epochs of the last exchange / barrier
     int ev_adv = 0;                      // epoch of the last advect (src_done / adv_done flags)
+    int ev_adv_waited = 0;               // newest advect epoch whose adv_done of EVERY rank this stream has waited for
     int* adv_block_flag = nullptr;       // per-block "has remote cells" marks of the two-pass advect
     size_t adv_blocks = 0;
 };
@@ -79,8 +80,18 @@ struct FieldSet {
     // lazily right before the step first overwrites u or v instead of at the step's start.
     std::vector<cudaEvent_t> readers;
     int wait_readers() {
+        TRY(quiesce_gathers());
         for (cudaEvent_t e : readers) CU(cudaStreamWaitEvent(stream, e, 0));
         readers.clear();
+        return 0;
+    }
+    // Slab mode: other ranks gather from my fields during their advect (peer loads).  Before anything from
+    // outside the step schedule writes a field (upload, fill, inject), wait until every rank has finished the
+    // last advect; inside the schedule the same wait rides in a halo exchange (exchange(.., wait_adv_event)).
+    int quiesce_gathers() {
+        if (!is_slab() || slab.ev_adv <= slab.ev_adv_waited) return 0;
+        TRY(wait_all(1, slab.ev_adv));
+        slab.ev_adv_waited = slab.ev_adv;
         return 0;
     }
 
@@ -301,6 +312,7 @@ struct FieldSet {
         PullArgs A{};
         A.wait_adv_event = wait_adv_event;
         A.world = slab.world;
+        if (wait_adv_event > slab.ev_adv_waited) slab.ev_adv_waited = wait_adv_event;
         const int me = slab.rank;
         A.me = me; A.pitch = g.pitch; A.event = ++slab.ev_pull;
         A.nbr[0] = me > 0 ? me - 1 : -1;
@@ -345,15 +357,6 @@ struct FieldSet {
         A.event = ++slab.ev_bar; A.me = slab.rank; A.world = slab.world; A.mine = flags(slab.rank);
         for (int r = 0; r < slab.world; ++r) A.peer[r] = flags(r);
         LAUNCH("k_slab_barrier", stream, (k_slab_barrier<<<1, 32, 0, stream>>>(A)));
-        return 0;
-    }
-    // "I have finished writing the fields the next advect gathers from" (which = 0) / "I have finished
-    // that advect" (which = 1): broadcast to every rank, nobody waits here.
-    int signal_all(int which) {
-        SignalArgs A{};
-        A.event = slab.ev_adv; A.me = slab.rank; A.world = slab.world; A.which = which; A.mine = flags(slab.rank);
-        for (int r = 0; r < slab.world; ++r) A.peer[r] = flags(r);
-        LAUNCH("k_slab_signal_all", stream, (k_slab_signal_all<<<1, 32, 0, stream>>>(A)));
         return 0;
     }
     // Wait until every rank has signalled `which` for advect epoch `event` (before overwriting gathered fields).

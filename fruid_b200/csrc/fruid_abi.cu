@@ -187,6 +187,7 @@ extern "C" int fruid_density_fill(fruid_density_t* d, int field, float val) {
     NEED(d);
     FieldSet& s = d->s;
     if (field < 0 || field > 1) return fail(FRUID_ERR_BAD_ARG, "bad field %d", field);
+    TRY(s.wait_readers());
     if (val == 0.0f && !std::signbit(val)) {
         CU(cudaMemsetAsync(s.buf[field], 0, s.g.pitch * (size_t)s.g.h * sizeof(float), s.stream));
         return 0;

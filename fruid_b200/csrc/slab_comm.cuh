@@ -136,21 +136,15 @@ __global__ void k_slab_pull(const __grid_constant__ PullArgs A) {
 
 // "Lazy" all-rank synchronisation around the peer gathers of advect: instead of two barriers,
 // every rank BROADCASTS an epoch (no waiting) when it has finished writing the gathered fields
-// (src_done) and when it has finished its advect (adv_done); a gathering thread waits only for the
-// OWNER of a remote tap (k_advect4 pass 2), and a rank waits for everybody's adv_done only right
-// before it overwrites the gathered fields -- by then the flags have long arrived.
+// (src_done, by k_advect4 pass 1) and when it has finished its advect (adv_done, by the last block of
+// pass 2); a gathering thread waits only for the OWNER of a remote tap (pass 2), and a rank waits for
+// everybody's adv_done only right before it overwrites the gathered fields -- inside the next halo
+// exchange (k_slab_pull), or with k_slab_wait_all ahead of an upload / fill / inject.
 struct SignalArgs {
     int event, me, world, which;   // which: 0 = src_done, 1 = adv_done
     SlabFlags* mine;
     SlabFlags* peer[SLAB_MAX_RANKS];
 };
-__global__ void k_slab_signal_all(const __grid_constant__ SignalArgs A) {
-    const int t = threadIdx.x;
-    if (t < A.world) {
-        int* flag = A.which == 0 ? &A.peer[t]->src_done[A.me] : &A.peer[t]->adv_done[A.me];
-        st_release_sys(flag, A.event);  // release: everything this stream wrote before is visible first
-    }
-}
 __global__ void k_slab_wait_all(const __grid_constant__ SignalArgs A) {
     const int t = threadIdx.x;
     if (t < A.world && t != A.me)

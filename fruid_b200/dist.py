@@ -121,6 +121,14 @@ class SlabDensitySim:
         self._lib.check(self._lib.lib.fruid_density_download(self._h, field, self._lib.ptr(out)))
         return out
 
+    def fill(self, field: int, val: float) -> None:
+        """`density_mut().data_mut().fill(val)` (main.rs:105-108) on every rank's rows."""
+        self._lib.check(self._lib.lib.fruid_density_fill(self._h, field, val))
+
+    def inject(self, field: int, x: int, y: int, val: float) -> None:
+        """One-cell write at GLOBAL (x, y); every rank calls it, the owner of the row performs it."""
+        self._lib.check(self._lib.lib.fruid_density_inject(self._h, field, x, y, val))
+
     def set_iterations(self, k: int) -> None:
         self._lib.check(self._lib.lib.fruid_density_set_iterations(self._h, k))
 

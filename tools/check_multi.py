@@ -27,6 +27,10 @@ ap.add_argument("--h", type=int, default=1536)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--cfl", type=float, default=40.0)
 ap.add_argument("--visc", type=float, default=1e-6)
+ap.add_argument("--frame-inputs", action="store_true",
+                help="between steps write sources like the reference's frame loop (main.rs:98-108): two velocity cells next "
+                     "to a slab cut, dens_prev filled with 0 plus one dye cell -- host writes while other ranks may still "
+                     "be gathering from the fields")
 args = ap.parse_args()
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -42,7 +46,20 @@ for name, field in (("u", 0), ("v", 1), ("u_prev", 2), ("v_prev", 3)):
 for name, field in (("dens", 0), ("dens_prev", 1)):
     den.upload(field, sc[name])
 dist.barrier()
-for _ in range(args.steps):
+def frame_inputs(k, inject_u, inject_d, fill_d):
+    """The per-frame source writes; the same global cells for the slab run and the single-GPU run."""
+    cut = (h // world) if world > 1 else h // 2
+    x = (w // 3 + 17 * k) % (w - 2) + 1
+    for dy in (-1, 0):                      # the rows on either side of the first slab cut
+        inject_u(2, x, cut + dy, -4500.0 + k)
+        inject_u(3, x, cut + dy, 3000.0 - k)
+    fill_d(1, 0.0)
+    inject_d(1, x, cut - 1, 80.0 * 250 * 250)
+
+
+for k in range(args.steps):
+    if args.frame_inputs:
+        frame_inputs(k, sim.inject, den.inject, den.fill)
     sim.step(DT, args.visc)
     den.step(sim, DT, args.visc)
 sim.sync()
@@ -61,7 +78,11 @@ if rank == 0:
         _lib.check(_lib.lib.fruid_fluid_upload(s1._h, field, _lib.ptr(full[name])))
     for name, field in (("dens", 0), ("dens_prev", 1)):
         _lib.check(_lib.lib.fruid_density_upload(d1._h, field, _lib.ptr(full[name])))
-    for _ in range(args.steps):
+    for k in range(args.steps):
+        if args.frame_inputs:
+            frame_inputs(k, lambda f, x, y, v: _lib.check(_lib.lib.fruid_fluid_inject(s1._h, f, x, y, v)),
+                         lambda f, x, y, v: _lib.check(_lib.lib.fruid_density_inject(d1._h, f, x, y, v)),
+                         lambda f, v: _lib.check(_lib.lib.fruid_density_fill(d1._h, f, v)))
         _lib.check(_lib.lib.fruid_fluid_step(s1._h, DT, args.visc))
         _lib.check(_lib.lib.fruid_density_step_dev(d1._h, s1._h, DT, args.visc))
     ref = []
