@@ -5,6 +5,9 @@ allocation at start-up (and for the bench's barriers); all data-path traffic -- 
 advection gathers -- moves over NVLink peer memory inside the library's own kernels
 (fruid_b200/csrc/slab_comm.cuh).  Pure partition arithmetic lives in `partition()` so that it can
 be tested on CPU (tests/test_slab_cpu.py, gloo world_size 2).
+
+Teardown is collective: call `sync()` on every rank and then `torch.distributed.barrier()` before the
+objects are dropped -- a neighbour may otherwise still be reading the memory a faster rank frees.
 """
 from __future__ import annotations
 

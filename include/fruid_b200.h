@@ -168,7 +168,10 @@ int fruid_draw_velocity_lines(fruid_fluid_t *f, float z, float *host_vertices);
  * on one GPU with halo rows pulled over NVLink and advection gathers served from the owner's
  * memory; results are bit-identical to the single-GPU run.  upload/download move the OWNED rows
  * (dense w floats per row); inject takes global coordinates.  Every rank must issue the same
- * sequence of step calls. */
+ * sequence of step calls.  Teardown is collective as well: a rank may destroy a slab handle only
+ * after ALL ranks have finished their work on it (fruid_*_sync on every rank, then a barrier of
+ * the host-side process group) -- until then a neighbour may still be pulling halo rows or
+ * gathering advection taps from the memory being freed. */
 int fruid_fluid_create_slab(size_t w, size_t gh, int rank, int world, fruid_fluid_t **out);
 int fruid_fluid_ipc_export(fruid_fluid_t *f, void *handle64);
 int fruid_fluid_ipc_attach(fruid_fluid_t *f, int peer_rank, const void *handle64);
