@@ -477,34 +477,59 @@ def run_b200_multi(args, fb, dist, rank, world, local):
     per_rank_split = [None] * world
     dist.all_gather_object(per_rank_split, (compute_ms, comm_ms))
 
-    # end to end: every step each rank uploads its rows of the three source fields and downloads
-    # its rows of the density (host <-> device inside the timed region), wall clock, max over ranks
+    # end to end: every step each rank uploads its rows of the three source fields and downloads its rows
+    # of the density (host <-> device inside the timed region), wall clock, max over ranks.  Like the
+    # single-GPU leg: asynchronous transfers that overlap the neighbouring steps (value) and the blocking
+    # upload / step / download sequence (serial_value).
     rows = sim.y1 - sim.y0
-    host = {k: np.ascontiguousarray(sc[k]) for k in ("u_prev", "v_prev", "dens_prev")}
-    out = np.empty((rows, w), np.float32)
-    pinned = [a for a in (*host.values(), out) if L.fruid_host_register(a.ctypes.data, a.nbytes) == 0]
+    host = [{k: np.ascontiguousarray(sc[k]).copy() for k in ("u_prev", "v_prev", "dens_prev")} for _ in range(2)]
+    out = [np.empty((rows, w), np.float32) for _ in range(2)]
+    arrays = [a for hs in host for a in hs.values()] + out
+    pinned = [a for a in arrays if L.fruid_host_register(a.ctypes.data, a.nbytes) == 0]
 
-    def e2e_step():
-        sim.upload(_lib.U_PREV, host["u_prev"])
-        sim.upload(_lib.V_PREV, host["v_prev"])
-        den.upload(_lib.DENS_PREV, host["dens_prev"])
-        scene_step()
-        _lib.check(L.fruid_density_download(den._h, _lib.DENS, _lib.ptr(out)))
+    def push(i):
+        hs = host[i & 1]
+        _lib.check(L.fruid_fluid_upload_async(sim._h, _lib.U_PREV, _lib.ptr(hs["u_prev"])))
+        _lib.check(L.fruid_fluid_upload_async(sim._h, _lib.V_PREV, _lib.ptr(hs["v_prev"])))
+        _lib.check(L.fruid_density_upload_async(den._h, _lib.DENS_PREV, _lib.ptr(hs["dens_prev"])))
 
-    e2e_step()
-    torch.cuda.synchronize(); dist.barrier()
-    n = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(n):
-        e2e_step()
-    torch.cuda.synchronize(); dist.barrier()
-    sec = torch.tensor([time.perf_counter() - t0], device="cuda")
-    dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+    def pipelined(n):
+        push(0)
+        for i in range(n):
+            scene_step()                                                   # consumes the staged sources
+            if i + 1 < n:
+                push(i + 1)                                                # h2d behind step i's kernels
+            _lib.check(L.fruid_density_download_async(den._h, _lib.DENS, _lib.ptr(out[i & 1])))  # d2h behind step i+1
+        sim.sync()
+        den.sync()
+
+    def serial(n):
+        for i in range(n):
+            hs = host[i & 1]
+            sim.upload(_lib.U_PREV, hs["u_prev"])
+            sim.upload(_lib.V_PREV, hs["v_prev"])
+            den.upload(_lib.DENS_PREV, hs["dens_prev"])
+            scene_step()
+            _lib.check(L.fruid_density_download(den._h, _lib.DENS, _lib.ptr(out[i & 1])))
+
+    n = max(2, min(args.steps, 10))
+    res = {}
+    for name, fn in (("pipelined", pipelined), ("serial", serial)):
+        fn(2)
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        fn(n)
+        torch.cuda.synchronize(); dist.barrier()
+        sec = torch.tensor([time.perf_counter() - t0], device="cuda")
+        dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+        res[name] = w * h * n / float(sec.item())
     for a in pinned:
         L.fruid_host_unregister(a.ctypes.data)
-    e2e = {"value": w * h * n / float(sec.item()), "unit": "cell-steps/s", "h2d_bytes_per_step": 3 * w * h * 4,
-           "d2h_bytes_per_step": w * h * 4, "steps": n,
-           "note": "whole-job bytes; each rank moves its own rows (h2d of 3 source fields, d2h of density) every step"}
+    e2e = {"value": res["pipelined"], "unit": "cell-steps/s", "h2d_bytes_per_step": 3 * w * h * 4,
+           "d2h_bytes_per_step": w * h * 4, "steps": n, "serial_value": res["serial"],
+           "pinned_host": len(pinned) == len(arrays),
+           "note": "whole-job bytes; each rank moves its own rows (h2d of 3 source fields, d2h of density) every step; "
+                   "value = asynchronous (overlapped) transfers, serial_value = blocking upload/step/download"}
 
     if rank == 0:
         cfg = workload_config(args, world)
