@@ -86,6 +86,8 @@ SIGNATURES = {
     "fruid_density_step_dev": [_vp, _vp, _f, _f],
     "fruid_density_step_dev_batch": [_vp, _i, _vp, _f, _f],
     "fruid_density_step_host": [_vp, _vp, _vp, _f, _f],
+    "fruid_fluid_bind_mirror": [_vp, _i, _vp],
+    "fruid_host_velocity_uploads": [],
     "fruid_density_sync": [_vp],
     "fruid_draw_density": [_vp, _vp, _vp, _vp, _f, _vp],
     "fruid_density_colors": [_vp, _vp, _vp, _vp, _vp],
@@ -103,6 +105,7 @@ _RESTYPES = {
     "fruid_last_error": ctypes.c_char_p,
     "fruid_build_info": ctypes.c_char_p,
     "fruid_kernel_launch_count": ctypes.c_uint64,
+    "fruid_host_velocity_uploads": ctypes.c_uint64,
     "fruid_fluid_stream": _vp,
     "fruid_density_stream": _vp,
     "fruid_fluid_width": _sz,

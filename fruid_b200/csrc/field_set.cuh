@@ -72,6 +72,13 @@ struct FieldSet {
     bool up_pending[4] = {false, false, false, false};
     float* dl_stage = nullptr;
     cudaEvent_t dl_snap = nullptr, dl_done = nullptr;                 // snapshot taken (compute) / downloaded (copy)
+    // Host mirrors (fruid_fluid_bind_mirror): the caller's arrays that shadow u and v.  A mirror is current while
+    // mirror_epoch == dev_epoch, i.e. it was downloaded after the last change of the device fields; then
+    // fruid_density_step_host(d, u, v, ..) with exactly these pointers can use the device-resident velocity.
+    uint64_t dev_epoch = 1;
+    const float* mirror[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t mirror_epoch[4] = {0, 0, 0, 0};
+    void touch() { ++dev_epoch; }
     int iters = 20;  // src/lib.rs:52
     int fused = 0;   // 0 = library default
     int device = 0;
@@ -172,6 +179,7 @@ struct FieldSet {
     int upload(int field, const float* host) {
         if (field < 0 || field >= n_user || !host) return fail(FRUID_ERR_BAD_ARG, "bad field %d or null host pointer", field);
         TRY(wait_readers());
+        touch();
         CU(cudaMemcpy2DAsync(buf[field] + (size_t)own_lo() * g.pitch, g.pitch * sizeof(float), host, (size_t)g.w * sizeof(float),
                              (size_t)g.w * sizeof(float), (size_t)(own_hi() - own_lo()), cudaMemcpyHostToDevice, stream));
         CU(cudaStreamSynchronize(stream));  // host buffer may be pageable and reused by the caller
@@ -182,6 +190,7 @@ struct FieldSet {
         CU(cudaMemcpy2DAsync(host, (size_t)g.w * sizeof(float), buf[field] + (size_t)own_lo() * g.pitch, g.pitch * sizeof(float),
                              (size_t)g.w * sizeof(float), (size_t)(own_hi() - own_lo()), cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
+        if (host == mirror[field]) mirror_epoch[field] = dev_epoch;
         return check_peer_error();
     }
     int ensure_copy_stream() {
@@ -193,6 +202,7 @@ struct FieldSet {
     int upload_async(int field, const float* host) {
         if (field < 0 || field >= n_user || !host) return fail(FRUID_ERR_BAD_ARG, "bad field %d or null host pointer", field);
         TRY(ensure_copy_stream());
+        touch();
         const size_t rows = (size_t)(own_hi() - own_lo());
         if (!up_stage[field]) {
             CU(cudaMalloc(&up_stage[field], g.pitch * rows * sizeof(float)));
@@ -253,6 +263,7 @@ struct FieldSet {
         if (field < 0 || field >= n_user) return fail(FRUID_ERR_BAD_ARG, "bad field %d", field);
         if (x >= (size_t)g.w || y >= (size_t)g.gh) return fail(FRUID_ERR_BAD_ARG, "cell (%zu,%zu) outside %dx%d", x, y, g.w, g.gh);
         const int ly = (int)y - g.gy0;
+        touch();
         if (ly < own_lo() || ly >= own_hi()) return 0;
         TRY(wait_readers());
         CU(cudaMemcpyAsync(buf[field] + x + (size_t)ly * g.pitch, &val, sizeof(float), cudaMemcpyHostToDevice, stream));

@@ -60,6 +60,11 @@ namespace { struct PdlEnv { PdlEnv() { if (const char* e = getenv("FRUID_B200_LA
 extern "C" int fruid_set_launch_overlap(int on) { g_pdl_enabled = on != 0; g_cfg_epoch.fetch_add(1); return 0; }
 extern "C" int fruid_set_graphs_enabled(int on) { g_graphs_enabled = on != 0; g_cfg_epoch.fetch_add(1); return 0; }
 
+// Live single-process registry of velocity handles: fruid_density_step_host looks its (u, v) pointers up here.
+static std::mutex g_fluids_mu;
+static std::vector<fruid_fluid*> g_fluids;
+static std::atomic<uint64_t> g_velocity_uploads{0};
+
 #define NEED(h) do { if (!(h)) return fail(FRUID_ERR_BAD_ARG, "null handle"); CU(cudaSetDevice((h)->s.device)); } while (0)
 
 extern "C" int fruid_fluid_create(size_t w, size_t h, fruid_fluid_t** out) {
@@ -69,6 +74,7 @@ extern "C" int fruid_fluid_create(size_t w, size_t h, fruid_fluid_t** out) {
     if (!f) return fail(FRUID_ERR_OOM, "host allocation failed");
     int r = f->s.init(w, h, 6);
     if (r) { f->s.release(); delete f; return r; }
+    { std::lock_guard<std::mutex> lk(g_fluids_mu); g_fluids.push_back(f); }
     *out = f;
     return 0;
 }
@@ -111,6 +117,10 @@ extern "C" int fruid_fluid_debug_barrier(fruid_fluid_t* f, int n) {
 }
 extern "C" int fruid_fluid_destroy(fruid_fluid_t* f) {
     if (!f) return 0;
+    {
+        std::lock_guard<std::mutex> lk(g_fluids_mu);
+        g_fluids.erase(std::remove(g_fluids.begin(), g_fluids.end(), f), g_fluids.end());
+    }
     cudaSetDevice(f->s.device);
     f->s.release();
     delete f;
@@ -128,9 +138,20 @@ extern "C" int fruid_fluid_download_async(fruid_fluid_t* f, int field, float* ho
 extern "C" int fruid_fluid_inject(fruid_fluid_t* f, int field, size_t x, size_t y, float val) { NEED(f); return f->s.inject(field, x, y, val); }
 extern "C" int fruid_fluid_set_iterations(fruid_fluid_t* f, int k) { NEED(f); return f->s.set_iters(k); }
 extern "C" int fruid_fluid_set_fused_sweeps(fruid_fluid_t* f, int t) { NEED(f); return f->s.set_fused(t); }
+// The caller's host arrays that shadow field `field` (the Array2D inside the crate-API mirror).
+extern "C" int fruid_fluid_bind_mirror(fruid_fluid_t* f, int field, const float* host) {
+    NEED(f);
+    if (field < 0 || field >= f->s.n_user) return fail(FRUID_ERR_BAD_ARG, "bad field %d", field);
+    std::lock_guard<std::mutex> lk(g_fluids_mu);
+    f->s.mirror[field] = host;
+    f->s.mirror_epoch[field] = 0;
+    return 0;
+}
+extern "C" uint64_t fruid_host_velocity_uploads(void) { return g_velocity_uploads.load(); }
 extern "C" int fruid_fluid_step(fruid_fluid_t* f, float dt, float visc) {
     NEED(f);
     FieldSet& s = f->s;
+    s.touch();
     TRY(s.consume_uploads());
     if (s.is_slab()) return op_vel_step_slab(s, visc, dt);
     return run_step_graphed(s, dt, visc, nullptr, nullptr, [&]() {
@@ -299,6 +320,20 @@ extern "C" int fruid_density_step_host(fruid_density_t* d, const float* u, const
     NEED(d);
     if (!u || !v) return fail(FRUID_ERR_BAD_ARG, "null velocity pointer");
     FieldSet& s = d->s;
+    {   // (u, v) = the current host mirrors of a live FluidSim (the c.step(sim.uv(), ..) pattern, main.rs:115)?
+        fruid_fluid* vel = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g_fluids_mu);
+            for (fruid_fluid* f : g_fluids) {
+                const FieldSet& fs = f->s;
+                if (fs.mirror[FRUID_U] == u && fs.mirror[FRUID_V] == v && fs.mirror_epoch[FRUID_U] == fs.dev_epoch &&
+                    fs.mirror_epoch[FRUID_V] == fs.dev_epoch && !fs.is_slab() && fs.device == s.device && fs.g.w == s.g.w &&
+                    fs.g.gh == s.g.gh) { vel = f; break; }
+            }
+        }
+        if (vel) return fruid_density_step_dev(d, vel, dt, diff);  // device-resident velocity: nothing to upload
+    }
+    g_velocity_uploads.fetch_add(1);
     if (s.is_slab()) return fail(FRUID_ERR_BAD_ARG, "slab-decomposed density needs a device-resident velocity (fruid_density_step_dev)");
     const size_t bytes = s.g.pitch * (size_t)s.g.h * sizeof(float);
     float *du = nullptr, *dv = nullptr;

@@ -59,6 +59,9 @@ public:
     FluidSim(std::size_t width, std::size_t height)  // FluidSim::new, lib.rs:256
         : u_(width, height), v_(width, height), u_prev_(width, height), v_prev_(width, height) {
         check(fruid_fluid_create(width, height, &h_));
+        // uv() hands out these two arrays: c.step(sim.uv(), ..) then finds the velocity on the device
+        check(fruid_fluid_bind_mirror(h_, FRUID_U, u_.data().data()));
+        check(fruid_fluid_bind_mirror(h_, FRUID_V, v_.data().data()));
     }
     ~FluidSim() { fruid_fluid_destroy(h_); }
     FluidSim(const FluidSim&) = delete;
@@ -117,7 +120,8 @@ public:
         check(fruid_density_step_dev(h_, vel.handle(), dt, diff));
         dens_stale_ = prev_stale_ = true;
     }
-    // Same with caller-owned host velocity fields (any Array2D pair).
+    // The literal reference signature, c.step(sim.uv(), dt, diff) (lib.rs:226, main.rs:115): when the pair is a
+    // FluidSim's current uv() the library uses the device-resident velocity, otherwise it uploads the arrays.
     void step(std::pair<const Array2D&, const Array2D&> uv, float dt, float diff) {
         push();
         check(fruid_density_step_host(h_, uv.first.data().data(), uv.second.data().data(), dt, diff));

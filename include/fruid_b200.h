@@ -141,8 +141,18 @@ int fruid_density_step_dev(fruid_density_t *d, fruid_fluid_t *vel, float dt, flo
  * as one call.  Results are those of n fruid_density_step_dev calls, bit for bit; the dyes'
  * diffuses run concurrently and one advect launch moves up to four dyes with a shared back-trace. */
 int fruid_density_step_dev_batch(fruid_density_t *const *dyes, int n, fruid_fluid_t *vel, float dt, float diff);
-/* Same, with (u, v) given as host arrays (uploaded first). */
+/* Same, with (u, v) given as host arrays, the literal signature of lib.rs:226.  If (u, v) are exactly the
+ * arrays bound with fruid_fluid_bind_mirror as the U and V mirrors of a live velocity handle, and both were
+ * downloaded after that handle's last change (step, upload, inject), the device-resident velocity is used
+ * and nothing is uploaded -- so the reference's `c.step(sim.uv(), dt, diff)` costs no PCIe traffic through a
+ * shim that knows nothing about the pairing.  Otherwise the arrays are uploaded first. */
 int fruid_density_step_host(fruid_density_t *d, const float *u, const float *v, float dt, float diff);
+/* Declares `host` (w*h floats, caller-owned, alive until rebound or the handle is destroyed) to be the
+ * caller's mirror of `field`: the array the crate-API shim hands out from uv() / uv_mut().  Its contents must
+ * change only through fruid_fluid_download.  See fruid_density_step_host. */
+int fruid_fluid_bind_mirror(fruid_fluid_t *f, int field, const float *host);
+/* How many times fruid_density_step_host had to upload a velocity pair (diagnostics / tests). */
+uint64_t fruid_host_velocity_uploads(void);
 int fruid_density_sync(fruid_density_t *d);
 void *fruid_density_stream(fruid_density_t *d);
 

@@ -25,6 +25,7 @@ extern "C" {
     fn fruid_density_upload(d: *mut FruidDensity, field: c_int, host: *const f32) -> c_int;
     fn fruid_density_download(d: *mut FruidDensity, field: c_int, host: *mut f32) -> c_int;
     fn fruid_density_step_host(d: *mut FruidDensity, u: *const f32, v: *const f32, dt: f32, diff: f32) -> c_int;
+    fn fruid_fluid_bind_mirror(f: *mut FruidFluid, field: c_int, host: *const f32) -> c_int;
     fn fruid_host_register(p: *mut std::ffi::c_void, bytes: usize) -> c_int;
     fn fruid_host_unregister(p: *mut std::ffi::c_void) -> c_int;
 }
@@ -71,8 +72,9 @@ impl DensitySim {
             check(unsafe { fruid_density_upload(self.handle, DENS_PREV, self.dens_prev.data().as_ptr()) });
             self.prev_dirty = false;
         }
-        // (u, v) are host arrays here; a FluidSim-aware fast path would call fruid_density_step_dev
-        // after matching u.data().as_ptr() against the registry of live FluidSim mirrors.
+        // (u, v) are host arrays here.  When they are a live FluidSim's uv() -- `c.step(sim.uv(), ..)`, reference
+        // src/main.rs:115 -- the library recognises the bound mirror pointers (fruid_fluid_bind_mirror in
+        // FluidSim::new) and uses the device-resident velocity; any other pair is uploaded.
         check(unsafe { fruid_density_step_host(self.handle, u.data().as_ptr(), v.data().as_ptr(), dt, diff) });
         self.dens_stale.set(true);
         self.prev_stale = true;
@@ -120,6 +122,9 @@ impl FluidSim {
         let mut s = Self { u: UnsafeCell::new(arr()), v: UnsafeCell::new(arr()), u_prev: arr(), v_prev: arr(), handle,
                            uv_stale: Cell::new(false), prev_stale: false, prev_dirty: false };
         pin(s.u.get_mut()); pin(s.v.get_mut()); pin(&mut s.u_prev); pin(&mut s.v_prev);
+        // the Vec buffers never move: uv() always hands out these two arrays (see DensitySim::step)
+        check(unsafe { fruid_fluid_bind_mirror(s.handle, U, s.u.get_mut().data().as_ptr()) });
+        check(unsafe { fruid_fluid_bind_mirror(s.handle, V, s.v.get_mut().data().as_ptr()) });
         s
     }
 

@@ -12,6 +12,9 @@ int main() {
         c.density_mut()[{20, 24}] = 80.0f * 64 * 48;
         sim.step(0.1f, 0.0f);
         c.step(sim, 0.1f, 0.0f);
+        const unsigned long long up0 = fruid_host_velocity_uploads();
+        c.step(sim.uv(), 1e-2f, 0.0f);  // the reference's own call shape (main.rs:115): must not upload u, v
+        if (fruid_host_velocity_uploads() != up0) { std::printf("c.step(sim.uv(), ..) uploaded the velocity\n"); return 1; }
         fruid::DensitySim m(sim.width(), sim.height());
         fruid::DensitySim::step_all({&c, &m}, sim, 1e-2f, 0.0f);  // main.rs:114-118, batched
         auto [u, v] = sim.uv();

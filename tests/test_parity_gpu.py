@@ -350,6 +350,64 @@ def test_density_step_with_host_velocity(fb, oracle_mod):
     assert_bits(den.density_mut().numpy(), od.dens_prev, "dens_prev")
 
 
+def test_step_host_recognises_bound_velocity_mirrors(fb, oracle_mod):
+    """`c.step(sim.uv(), dt, diff)` through the literal host-array signature (lib.rs:226).  With the
+    (u, v) arrays bound as the FluidSim's mirrors and downloaded after its last change, the library uses the
+    device-resident velocity (no upload); stale or foreign arrays are uploaded and used as given."""
+    L = fb._lib.lib
+    w, h = 120, 90
+    rng = np.random.default_rng(21)
+    sim, den, osim, oden = fb.FluidSim(w, h), fb.DensitySim(w, h), oracle_mod.Fluid(w, h), oracle_mod.Density(w, h)
+    for name, field in (("u_prev", 2), ("v_prev", 3)):
+        a = rand_field(rng, w, h, 30.0)
+        getattr(osim, name)[:] = a
+        fb._lib.check(L.fruid_fluid_upload(sim._h, field, fb._lib.ptr(a)))
+    src = rand_field(rng, w, h)
+    oden.dens_prev[:] = src
+    fb._lib.check(L.fruid_density_upload(den._h, 1, fb._lib.ptr(src)))
+    u, v = np.zeros((h, w), np.float32), np.zeros((h, w), np.float32)
+    fb._lib.check(L.fruid_fluid_bind_mirror(sim._h, 0, fb._lib.ptr(u)))
+    fb._lib.check(L.fruid_fluid_bind_mirror(sim._h, 1, fb._lib.ptr(v)))
+
+    def uploads():
+        return int(L.fruid_host_velocity_uploads())
+
+    # never downloaded: the (zero) host arrays are what the caller means -> uploaded
+    n0 = uploads()
+    fb._lib.check(L.fruid_density_step_host(den._h, fb._lib.ptr(u), fb._lib.ptr(v), 0.05, 0.0))
+    oden.step((u, v), 0.05, 0.0)
+    assert uploads() == n0 + 1
+    # step, download into the mirrors, step the dye: device velocity, no upload
+    fb._lib.check(L.fruid_fluid_step(sim._h, 0.05, 0.0))
+    osim.step(0.05, 0.0)
+    fb._lib.check(L.fruid_fluid_download(sim._h, 0, fb._lib.ptr(u)))
+    fb._lib.check(L.fruid_fluid_download(sim._h, 1, fb._lib.ptr(v)))
+    assert_bits(u, osim.u, "u")
+    for _ in range(2):
+        fb._lib.check(L.fruid_density_step_host(den._h, fb._lib.ptr(u), fb._lib.ptr(v), 0.05, 1e-4))
+        oden.step((osim.u, osim.v), 0.05, 1e-4)
+    assert uploads() == n0 + 1
+    # the velocity moves on but the mirrors are not refreshed: the call means the OLD velocity -> uploaded
+    fb._lib.check(L.fruid_fluid_step(sim._h, 0.05, 0.0))
+    fb._lib.check(L.fruid_density_step_host(den._h, fb._lib.ptr(u), fb._lib.ptr(v), 0.05, 0.0))
+    oden.step((u, v), 0.05, 0.0)
+    assert uploads() == n0 + 2
+    # foreign arrays with the same contents are uploaded too
+    u2, v2 = u.copy(), v.copy()
+    fb._lib.check(L.fruid_density_step_host(den._h, fb._lib.ptr(u2), fb._lib.ptr(v2), 0.05, 0.0))
+    oden.step((u2, v2), 0.05, 0.0)
+    assert uploads() == n0 + 3
+    got = np.empty((h, w), np.float32)
+    fb._lib.check(L.fruid_density_download(den._h, 0, fb._lib.ptr(got)))
+    assert_bits(got, oden.dens, "dens")
+    # an inject (uv_mut write) invalidates the mirrors until the next download
+    fb._lib.check(L.fruid_fluid_download(sim._h, 0, fb._lib.ptr(u)))
+    fb._lib.check(L.fruid_fluid_download(sim._h, 1, fb._lib.ptr(v)))
+    fb._lib.check(L.fruid_fluid_inject(sim._h, 0, 5, 5, 1.0))
+    fb._lib.check(L.fruid_density_step_host(den._h, fb._lib.ptr(u), fb._lib.ptr(v), 0.05, 0.0))
+    assert uploads() == n0 + 4
+
+
 def test_api_mirror_semantics(fb):
     """uv_mut() exposes (u_prev, v_prev); single-cell writes reach the device; size mismatch
     is an error instead of the reference's out-of-bounds panic (lib.rs:226)."""
