@@ -568,6 +568,67 @@ def test_automatic_tile_shape_on_small_grids(fb, oracle_mod, n, visc):
             assert_bits(g, want, name)
 
 
+TILE_SHAPES = [(8, 16), (10, 16), (6, 16), (6, 20), (7, 20), (5, 24), (4, 24), (8, 12), (4, 16), (2, 32), (2, 16), (4, 8), (3, 16)]
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_random_configurations(fb, oracle_mod, seed):
+    """Randomised sweep over what the fixed cases pin one at a time: grid shape (2..700, any remainder modulo the
+    4-cell vector, the 32-float pitch and the 128-wide tile), sweep count, fused depth, pinned or automatic tile shape,
+    viscosity regime, CFL, dye count (batched) and number of steps; every field against the oracle, bit for bit."""
+    rng = np.random.default_rng(1000 + seed)
+    w = int(rng.integers(2, 700)) if seed % 4 else int(rng.integers(2, 40))
+    h = int(rng.integers(2, 700)) if seed % 3 else int(rng.integers(2, 40))
+    iters = int(rng.choice([2, 4, 6, 10, 20, 20, 20, 26, 40]))
+    visc = float(rng.choice([0.0, 0.0, 1e-6, 3e-5, 2e-3]))
+    diff = float(rng.choice([0.0, 1e-6, 5e-4]))
+    dt = float(rng.choice([0.01, 0.1, 0.003]))
+    speed = float(rng.choice([0.5, 20.0, 4500.0]))
+    steps = int(rng.integers(1, 4))
+    ndyes = int(rng.integers(1, 5))
+    L = fb._lib.lib
+    pin = TILE_SHAPES[int(rng.integers(len(TILE_SHAPES)))] if seed % 2 else None
+    max_t = 0 if pin is None else (((min(pin[0] * pin[1], 128) // 2) - 2) & ~1)
+    fused = int(rng.choice([0, 0, 2, 4, 6, 10, 20]))
+    if pin is not None and fused > max_t:
+        fused = 0
+    sim, osim = fb.FluidSim(w, h), oracle_mod.Fluid(w, h, iters=iters)
+    dyes = [fb.DensitySim(w, h) for _ in range(ndyes)]
+    odyes = [oracle_mod.Density(w, h, iters=iters) for _ in range(ndyes)]
+    try:
+        if pin is not None:
+            fb._lib.check(L.fruid_set_tile_config(pin[0], pin[1], 0))
+        sim.set_iterations(iters)
+        sim.set_fused_sweeps(fused)
+        for name, field in (("u", 0), ("v", 1), ("u_prev", 2), ("v_prev", 3)):
+            a = rand_field(rng, w, h, speed)
+            getattr(osim, name)[:] = a
+            fb._lib.check(L.fruid_fluid_upload(sim._h, field, fb._lib.ptr(a)))
+        for d, od in zip(dyes, odyes):
+            d.set_iterations(iters)
+            d.set_fused_sweeps(fused)
+            for name, field in (("dens", 0), ("dens_prev", 1)):
+                a = rand_field(rng, w, h)
+                getattr(od, name)[:] = a
+                fb._lib.check(L.fruid_density_upload(d._h, field, fb._lib.ptr(a)))
+        for _ in range(steps):
+            sim.step(dt, visc)
+            fb.DensitySim.step_all(dyes, sim.uv(), dt, diff)
+    finally:
+        fb._lib.check(L.fruid_set_tile_config(0, 0, 10))
+    for _ in range(steps):
+        osim.step(dt, visc)
+        for od in odyes:
+            od.step((osim.u, osim.v), dt, diff)
+    tag = f"w={w} h={h} iters={iters} fused={fused} pin={pin} visc={visc} diff={diff} dt={dt} steps={steps} dyes={ndyes}"
+    got = [sim.uv()[0].numpy(), sim.uv()[1].numpy(), sim.uv_mut()[0].numpy(), sim.uv_mut()[1].numpy()]
+    for g, want, name in zip(got, (osim.u, osim.v, osim.u_prev, osim.v_prev), NAMES6):
+        assert_bits(g, want, f"{name} [{tag}]")
+    for i, (d, od) in enumerate(zip(dyes, odyes)):
+        assert_bits(d.density().numpy(), od.dens, f"dens{i} [{tag}]")
+        assert_bits(d.density_mut().numpy(), od.dens_prev, f"dens_prev{i} [{tag}]")
+
+
 @pytest.mark.parametrize("iters", [40, 100, 200, 500])
 def test_iteration_sweep_config3(fb, oracle_mod, iters):
     """BASELINE.json configs[3]: Jacobi-iteration sweep 20-500 (pressure-dominated regime), here on a
