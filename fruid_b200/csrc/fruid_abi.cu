@@ -229,15 +229,21 @@ extern "C" int fruid_density_step_dev(fruid_density_t* d, fruid_fluid_t* vel, fl
     TRY(s.consume_uploads());
     if (s.is_slab() != vs.is_slab() || s.slab.world != vs.slab.world || s.slab.rank != vs.slab.rank)
         return fail(FRUID_ERR_SIZE_MISMATCH, "density and velocity handles are decomposed differently");
-    // u,v are produced on vel's stream and consumed on ours; order both ways.
+    // u, v are produced on vel's stream and consumed on ours; order both ways.  Only the advect needs them:
+    // add_source + diffuse (lib.rs:172-175) start right away and run beside the velocity step still in flight.
     CU(cudaEventRecord(vs.ev, vs.stream));
-    if (!s.is_slab()) CU(cudaStreamWaitEvent(s.stream, vs.ev, 0));
-    if (s.is_slab())
+    if (s.is_slab()) {
         TRY(op_dens_step_slab(s, vs.buf[0], vs.buf[1], diff, dt, vs.ev));
-    else
-        TRY(run_step_graphed(s, dt, diff, vs.buf[0], vs.buf[1], [&]() {
-            return op_dens_step(s.buf[0], s.buf[1], vs.buf[0], vs.buf[1], s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream);
+    } else {
+        TRY(run_step_graphed(s, dt, diff, nullptr, nullptr, [&]() {
+            return op_add_source_diffuse(B_POSITIVE, s.buf[1], s.buf[0], s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream);
         }));
+        CU(cudaStreamWaitEvent(s.stream, vs.ev, 0));
+        float* dd[1] = {s.buf[0]};
+        const float* d0[1] = {s.buf[1]};
+        const int b[1] = {B_POSITIVE};
+        TRY(op_advect(1, dd, d0, b, vs.buf[0], vs.buf[1], s.g, dt, s.stream));  // lib.rs:178
+    }
     CU(cudaEventRecord(s.ev, s.stream));
     if (s.is_slab()) {
         if (std::find(vs.readers.begin(), vs.readers.end(), s.ev) == vs.readers.end()) vs.readers.push_back(s.ev);
@@ -247,10 +253,10 @@ extern "C" int fruid_density_step_dev(fruid_density_t* d, fruid_fluid_t* vel, fl
     return 0;
 }
 // Several dye fields advanced by one velocity field (the four DensitySims of main.rs:114-118): every
-// dye's add_source + diffuse runs on its own stream (concurrently on small grids), then ONE advect
-// launch moves up to four dyes with a shared back-trace (u, v are read once instead of once per dye).
-// Results are those of n separate fruid_density_step_dev calls, bit for bit.
-static int dens_step_batch_body(const std::vector<FieldSet*>& D, FieldSet& V, float dt, float diff) {
+// dye's add_source + diffuse runs on its own stream (concurrently on small grids; one captured graph with a
+// fork and a join), then ONE advect launch moves up to four dyes with a shared back-trace (u, v are read once
+// instead of once per dye).  Results are those of n separate fruid_density_step_dev calls, bit for bit.
+static int dens_diffuse_batch_body(const std::vector<FieldSet*>& D, float dt, float diff) {
     FieldSet& L = *D[0];
     CU(cudaEventRecord(L.ev_fork, L.stream));
     for (size_t i = 0; i < D.size(); ++i) {
@@ -262,6 +268,10 @@ static int dens_step_batch_body(const std::vector<FieldSet*>& D, FieldSet& V, fl
             CU(cudaStreamWaitEvent(L.stream, s.ev_join, 0));
         }
     }
+    return 0;
+}
+static int dens_advect_batch(const std::vector<FieldSet*>& D, FieldSet& V, float dt) {
+    FieldSet& L = *D[0];
     for (size_t i0 = 0; i0 < D.size(); i0 += ADVECT_MAX_FIELDS) {
         const int nf = (int)std::min<size_t>(ADVECT_MAX_FIELDS, D.size() - i0);
         float* d[ADVECT_MAX_FIELDS];
@@ -301,15 +311,17 @@ extern "C" int fruid_density_step_dev_batch(fruid_density_t* const* dyes, int n,
         D.push_back(&s);
         key.push_back(&s);
     }
-    // Everything is driven from the first dye's stream: it waits for the velocity step and for whatever
-    // is still queued on the other dyes' streams (uploads, injects, fills) ...
+    // Everything is driven from the first dye's stream: it waits for whatever is still queued on the other dyes'
+    // streams (uploads, injects, fills), runs the diffuses (beside the velocity step still in flight: only the
+    // advect needs u, v), waits for the velocity step, advects ...
     CU(cudaEventRecord(V.ev, V.stream));
-    CU(cudaStreamWaitEvent(L.stream, V.ev, 0));
     for (int i = 1; i < n; ++i) {
         CU(cudaEventRecord(D[i]->ev, D[i]->stream));
         CU(cudaStreamWaitEvent(L.stream, D[i]->ev, 0));
     }
-    TRY(run_graphed(L.batch_graph, L, D, dt, diff, V.buf[0], V.buf[1], key, [&]() { return dens_step_batch_body(D, V, dt, diff); }));
+    TRY(run_graphed(L.batch_graph, L, D, dt, diff, nullptr, nullptr, key, [&]() { return dens_diffuse_batch_body(D, dt, diff); }));
+    CU(cudaStreamWaitEvent(L.stream, V.ev, 0));
+    TRY(dens_advect_batch(D, V, dt));
     // ... and the other dyes' streams and the velocity stream continue after it.
     CU(cudaEventRecord(L.ev, L.stream));
     for (int i = 1; i < n; ++i) CU(cudaStreamWaitEvent(D[i]->stream, L.ev, 0));
