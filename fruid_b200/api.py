@@ -12,6 +12,8 @@ FluidSim and uses its device-resident velocity instead of uploading it again.
 """
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 
 from . import _lib
@@ -27,7 +29,9 @@ class Array2D:
     """
 
     def __init__(self, owner, field: int, width: int, height: int):
-        self._owner, self._field = owner, field
+        # weak: the simulation owns its mirrors, not the other way round -- no reference cycle, so dropping the
+        # last reference to a FluidSim / DensitySim releases its device memory right away (like Rust's Drop)
+        self._owner_ref, self._field = weakref.ref(owner), field
         self._w, self._h = width, height
         self._host = np.zeros((height, width), np.float32)
         # page-lock the mirror (fixed length for the object's life) so transfers run at PCIe rate
@@ -44,6 +48,13 @@ class Array2D:
                 lib.fruid_host_unregister(self._host_ptr)
             except Exception:  # interpreter shutdown
                 pass
+
+    @property
+    def _owner(self):
+        owner = self._owner_ref()
+        if owner is None:
+            raise ReferenceError("the simulation this Array2D belongs to has been dropped")
+        return owner
 
     def width(self) -> int:
         return self._w
@@ -212,9 +223,9 @@ class DensitySim:
         u, v = uv
         self._dens._push()
         self._dens_prev._push()
-        sim = getattr(u, "_owner", None)
+        sim = u._owner_ref() if isinstance(u, Array2D) else None
         if (isinstance(u, Array2D) and isinstance(v, Array2D) and isinstance(sim, FluidSim)
-                and v._owner is sim and u._field == _lib.U and v._field == _lib.V):
+                and v._owner_ref() is sim and u._field == _lib.U and v._field == _lib.V):
             u._push()
             v._push()
             check(lib.fruid_density_step_dev(self._h, sim._h, dt, diff))
@@ -233,9 +244,9 @@ class DensitySim:
         FluidSim's device-resident uv(); same results bit for bit."""
         dyes = list(dyes)
         u, v = uv
-        sim = getattr(u, "_owner", None)
+        sim = u._owner_ref() if isinstance(u, Array2D) else None
         if not (len(dyes) > 1 and isinstance(u, Array2D) and isinstance(v, Array2D) and isinstance(sim, FluidSim)
-                and v._owner is sim and u._field == _lib.U and v._field == _lib.V):
+                and v._owner_ref() is sim and u._field == _lib.U and v._field == _lib.V):
             for d in dyes:
                 d.step(uv, dt, diff)
             return

@@ -58,10 +58,11 @@ struct FieldSet {
     Geom g{};
     int n = 0;       // buffers allocated: user fields, then scratch (lib.rs:213,252), then the add_source temporary
     int n_user = 0;  // fields the crate API exposes
-    float* buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     char* base = nullptr;  // the one device allocation: [flag block][field 0][field 1]...
     size_t field_bytes = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // velocity handles: the v diffuse runs here beside the u diffuse (buf[6], buf[7])
     cudaEvent_t ev = nullptr;
     // Asynchronous transfers (pinned host memory): a copy stream, per-field upload staging buffers
     // and one download snapshot, so that PCIe traffic overlaps the kernels of the neighbouring steps.
@@ -117,7 +118,7 @@ struct FieldSet {
     float* peer_field(int r, int phys) const { return (float*)(slab.peer_base[r] + SLAB_FLAG_BYTES + (size_t)phys * peer_field_bytes(r)); }
     SlabFlags* flags(int r) const { return (SlabFlags*)slab.peer_base[r]; }
 
-    int init(size_t w, size_t gh, int nfields, int rank = 0, int world = 1) {
+    int init(size_t w, size_t gh, int nfields, int rank = 0, int world = 1, int extra = 0) {
         if (w < 2 || gh < 2) return fail(FRUID_ERR_BAD_SIZE, "grid must be at least 2x2 (got %zux%zu)", w, gh);
         if (w > (size_t)1 << 20 || gh > (size_t)1 << 20) return fail(FRUID_ERR_BAD_SIZE, "grid too large (%zux%zu)", w, gh);
         if (world < 1 || world > SLAB_MAX_RANKS || rank < 0 || rank >= world)
@@ -136,9 +137,10 @@ struct FieldSet {
             slab.rows[r] = hi - lo;
         }
         g = make_slab_geom(w, gh, pitch_for(w), slab.row0[rank], slab.rows[rank]);
-        n = nfields;
+        n = nfields + extra;
         n_user = nfields - 2;
         CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        if (extra) CU(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
@@ -173,6 +175,7 @@ struct FieldSet {
         if (ev) cudaEventDestroy(ev);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
+        if (stream2) { cudaStreamSynchronize(stream2); tile_sched_release(stream2); cudaStreamDestroy(stream2); }
         if (stream) { tile_sched_release(stream); cudaStreamDestroy(stream); }
     }
     // Host arrays cover the rows this rank OWNS (the whole field on one GPU), dense w floats per row.
@@ -406,7 +409,7 @@ struct FieldSet {
     const float* global_rows(const float* fp) const { return fp - (ptrdiff_t)g.gy0 * (ptrdiff_t)g.pitch; }
 };
 
-struct fruid_fluid { FieldSet s; };    // buf: 0=u 1=v 2=u_prev 3=v_prev 4=scratch (lib.rs:247-253) 5=add_source temporary
+struct fruid_fluid { FieldSet s; };    // buf: 0=u 1=v 2=u_prev 3=v_prev 4=scratch (lib.rs:247-253) 5=add_source temporary; single GPU: 6, 7 = the same two for the concurrent v diffuse
 struct fruid_density { FieldSet s; };  // buf: 0=dens 1=dens_prev 2=scratch (lib.rs:210-214) 3=add_source temporary
 
 
@@ -436,9 +439,9 @@ static int run_graphed(StepGraph& G, FieldSet& S, const std::vector<FieldSet*>& 
     if (G.failed) return body();
     // second step with the same parameters: capture it
     std::vector<float*> before;
-    for (FieldSet* P : parts) before.insert(before.end(), P->buf, P->buf + 6);
-    auto restore = [&]() { size_t k = 0; for (FieldSet* P : parts) for (int i = 0; i < 6; ++i) P->buf[i] = before[k++]; };
-    auto unchanged = [&]() { size_t k = 0; bool same = true; for (FieldSet* P : parts) for (int i = 0; i < 6; ++i) same &= (P->buf[i] == before[k++]); return same; };
+    for (FieldSet* P : parts) before.insert(before.end(), P->buf, P->buf + 8);
+    auto restore = [&]() { size_t k = 0; for (FieldSet* P : parts) for (int i = 0; i < 8; ++i) P->buf[i] = before[k++]; };
+    auto unchanged = [&]() { size_t k = 0; bool same = true; for (FieldSet* P : parts) for (int i = 0; i < 8; ++i) same &= (P->buf[i] == before[k++]); return same; };
     const uint64_t k0 = g_launches.load();
     if (cudaStreamBeginCapture(S.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
         cudaGetLastError();

@@ -56,7 +56,13 @@ extern "C" const char* fruid_build_info(void) { return "fruid_b200 0.1 (sm_100a,
 
 // Tuning / debugging knob: replay steps as CUDA graphs (default on).
 // Tuning / debugging knob: programmatic dependent launch between the kernels of a step (default on).
-namespace { struct PdlEnv { PdlEnv() { if (const char* e = getenv("FRUID_B200_LAUNCH_OVERLAP")) g_pdl_enabled = atoi(e) != 0; } } g_pdl_env; }
+static bool g_vel_fork = true;      // u and v diffuse on two streams
+static bool g_dens_overlap = true;  // density add_source + diffuse beside the velocity step
+namespace { struct PdlEnv { PdlEnv() {
+    if (const char* e = getenv("FRUID_B200_LAUNCH_OVERLAP")) g_pdl_enabled = atoi(e) != 0;
+    if (const char* e = getenv("FRUID_B200_VEL_FORK")) g_vel_fork = atoi(e) != 0;
+    if (const char* e = getenv("FRUID_B200_DENS_OVERLAP")) g_dens_overlap = atoi(e) != 0;
+} } g_pdl_env; }
 extern "C" int fruid_set_launch_overlap(int on) { g_pdl_enabled = on != 0; g_cfg_epoch.fetch_add(1); return 0; }
 extern "C" int fruid_set_graphs_enabled(int on) { g_graphs_enabled = on != 0; g_cfg_epoch.fetch_add(1); return 0; }
 
@@ -72,7 +78,7 @@ extern "C" int fruid_fluid_create(size_t w, size_t h, fruid_fluid_t** out) {
     *out = nullptr;
     fruid_fluid* f = new (std::nothrow) fruid_fluid();
     if (!f) return fail(FRUID_ERR_OOM, "host allocation failed");
-    int r = f->s.init(w, h, 6);
+    int r = f->s.init(w, h, 6, 0, 1, 2);  // + scratch and add_source temporary of the concurrent v diffuse
     if (r) { f->s.release(); delete f; return r; }
     { std::lock_guard<std::mutex> lk(g_fluids_mu); g_fluids.push_back(f); }
     *out = f;
@@ -155,7 +161,9 @@ extern "C" int fruid_fluid_step(fruid_fluid_t* f, float dt, float visc) {
     TRY(s.consume_uploads());
     if (s.is_slab()) return op_vel_step_slab(s, visc, dt);
     return run_step_graphed(s, dt, visc, nullptr, nullptr, [&]() {
-        return op_vel_step(s.buf[0], s.buf[1], s.buf[2], s.buf[3], s.buf[4], s.buf[5], s.g, visc, dt, s.iters, s.fused, s.stream);
+        VelFork fk{s.buf[6], s.buf[7], s.stream2, s.ev_fork, s.ev_join};
+        return op_vel_step(s.buf[0], s.buf[1], s.buf[2], s.buf[3], s.buf[4], s.buf[5], s.g, visc, dt, s.iters, s.fused, s.stream,
+                           (s.stream2 && g_vel_fork) ? &fk : nullptr);
     });
 }
 extern "C" int fruid_fluid_step_n(fruid_fluid_t* f, float dt, float visc, int n) {
@@ -235,6 +243,7 @@ extern "C" int fruid_density_step_dev(fruid_density_t* d, fruid_fluid_t* vel, fl
     if (s.is_slab()) {
         TRY(op_dens_step_slab(s, vs.buf[0], vs.buf[1], diff, dt, vs.ev));
     } else {
+        if (!g_dens_overlap) CU(cudaStreamWaitEvent(s.stream, vs.ev, 0));
         TRY(run_step_graphed(s, dt, diff, nullptr, nullptr, [&]() {
             return op_add_source_diffuse(B_POSITIVE, s.buf[1], s.buf[0], s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream);
         }));

@@ -601,7 +601,9 @@ static int* tile_sched_for(cudaStream_t st) {
     if (it != g_sched.end()) return it->second;
     int* p = nullptr;
     if (cudaMalloc(&p, 2 * sizeof(int)) != cudaSuccess) return nullptr;
-    if (cudaMemset(p, 0, 2 * sizeof(int)) != cudaSuccess) { cudaFree(p); return nullptr; }
+    // Zeroed ON THE STREAM that will use them: cudaMemset would run on the legacy default stream, which does not
+    // order with non-blocking streams -- the first kernel could read the words before they are cleared.
+    if (cudaMemsetAsync(p, 0, 2 * sizeof(int), st) != cudaSuccess) { cudaFree(p); return nullptr; }
     g_sched.emplace(st, p);
     return p;
 }

@@ -189,10 +189,27 @@ static int op_project(float* u, float* v, float*& p, float* div, float*& scratch
 
 // vel_step, src/lib.rs:181-208 (argument roles alternate exactly as in the reference;
 // no SWAPs -- lib.rs:193,196,201-202 are commented out there).
+// The two diffuses are independent (lib.rs:194 touches u*, lib.rs:197 v*): given a second stream and a second pair of
+// scratch buffers the v solve runs beside the u solve (on small grids a lone solve leaves most SMs idle).
+struct VelFork {
+    float*& scratch_v;
+    float* tmp_v;
+    cudaStream_t st2;
+    cudaEvent_t fork, join;
+};
 static int op_vel_step(float*& u, float*& v, float*& u0, float*& v0, float*& s, float* s2, const Geom& g, float visc,
-                       float dt, int iters, int fused, cudaStream_t st) {
-    TRY(op_add_source_diffuse(B_NEGX, u0, u, s, s2, g, visc, dt, iters, fused, st));  // lib.rs:190,194
-    TRY(op_add_source_diffuse(B_NEGY, v0, v, s, s2, g, visc, dt, iters, fused, st));  // lib.rs:191,197
+                       float dt, int iters, int fused, cudaStream_t st, VelFork* fk = nullptr) {
+    if (fk) {
+        CU(cudaEventRecord(fk->fork, st));
+        CU(cudaStreamWaitEvent(fk->st2, fk->fork, 0));
+        TRY(op_add_source_diffuse(B_NEGY, v0, v, fk->scratch_v, fk->tmp_v, g, visc, dt, iters, fused, fk->st2));  // lib.rs:191,197
+        CU(cudaEventRecord(fk->join, fk->st2));
+        TRY(op_add_source_diffuse(B_NEGX, u0, u, s, s2, g, visc, dt, iters, fused, st));                          // lib.rs:190,194
+        CU(cudaStreamWaitEvent(st, fk->join, 0));
+    } else {
+        TRY(op_add_source_diffuse(B_NEGX, u0, u, s, s2, g, visc, dt, iters, fused, st));  // lib.rs:190,194
+        TRY(op_add_source_diffuse(B_NEGY, v0, v, s, s2, g, visc, dt, iters, fused, st));  // lib.rs:191,197
+    }
     TRY(op_project(u0, v0, u, v, s, g, iters, fused, st));                  // lib.rs:199
     float* d[2] = {u, v};
     const float* d0[2] = {u0, v0};

@@ -50,3 +50,12 @@ def oracle_mod():
 
 def rand_field(rng, w, h, scale=1.0):
     return (rng.standard_normal((h, w)) * scale).astype(np.float32)
+
+
+@pytest.fixture(autouse=True)
+def _release_device_objects():
+    """Handles own device memory, streams and captured graphs: drop whatever a test left behind before the
+    next one starts, so that a test never runs concurrently with the teardown of its predecessor's objects."""
+    yield
+    import gc
+    gc.collect()
