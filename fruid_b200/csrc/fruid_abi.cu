@@ -57,7 +57,11 @@ extern "C" const char* fruid_build_info(void) { return "fruid_b200 0.1 (sm_100a,
 // Tuning / debugging knob: replay steps as CUDA graphs (default on).
 // Tuning / debugging knob: programmatic dependent launch between the kernels of a step (default on).
 static bool g_vel_fork = true;      // u and v diffuse on two streams
-static bool g_dens_overlap = true;  // density add_source + diffuse beside the velocity step
+// Density add_source + diffuse beside the velocity step still in flight (only the advect waits for u, v).  OFF by
+// default: with it the advect is launched directly after the replayed diffuse graph, and with that sequence the
+// test suite showed an intermittent mismatch (about 1 suite run in 12, rows 0-3 of one density field) that was not
+// tracked down; FRUID_B200_DENS_OVERLAP=1 turns it on (250^2 scene step 85 -> 70 us, 4096^2 1.15 -> 1.135 ms).
+static bool g_dens_overlap = false;
 namespace { struct PdlEnv { PdlEnv() {
     if (const char* e = getenv("FRUID_B200_LAUNCH_OVERLAP")) g_pdl_enabled = atoi(e) != 0;
     if (const char* e = getenv("FRUID_B200_VEL_FORK")) g_vel_fork = atoi(e) != 0;
@@ -242,8 +246,12 @@ extern "C" int fruid_density_step_dev(fruid_density_t* d, fruid_fluid_t* vel, fl
     CU(cudaEventRecord(vs.ev, vs.stream));
     if (s.is_slab()) {
         TRY(op_dens_step_slab(s, vs.buf[0], vs.buf[1], diff, dt, vs.ev));
+    } else if (!g_dens_overlap) {  // the whole step is one captured graph, after the velocity step
+        CU(cudaStreamWaitEvent(s.stream, vs.ev, 0));
+        TRY(run_step_graphed(s, dt, diff, vs.buf[0], vs.buf[1], [&]() {
+            return op_dens_step(s.buf[0], s.buf[1], vs.buf[0], vs.buf[1], s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream);
+        }));
     } else {
-        if (!g_dens_overlap) CU(cudaStreamWaitEvent(s.stream, vs.ev, 0));
         TRY(run_step_graphed(s, dt, diff, nullptr, nullptr, [&]() {
             return op_add_source_diffuse(B_POSITIVE, s.buf[1], s.buf[0], s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream);
         }));
@@ -328,9 +336,17 @@ extern "C" int fruid_density_step_dev_batch(fruid_density_t* const* dyes, int n,
         CU(cudaEventRecord(D[i]->ev, D[i]->stream));
         CU(cudaStreamWaitEvent(L.stream, D[i]->ev, 0));
     }
-    TRY(run_graphed(L.batch_graph, L, D, dt, diff, nullptr, nullptr, key, [&]() { return dens_diffuse_batch_body(D, dt, diff); }));
-    CU(cudaStreamWaitEvent(L.stream, V.ev, 0));
-    TRY(dens_advect_batch(D, V, dt));
+    if (!g_dens_overlap) {  // one captured graph: fork, diffuses, join, advect -- after the velocity step
+        CU(cudaStreamWaitEvent(L.stream, V.ev, 0));
+        TRY(run_graphed(L.batch_graph, L, D, dt, diff, V.buf[0], V.buf[1], key, [&]() {
+            TRY(dens_diffuse_batch_body(D, dt, diff));
+            return dens_advect_batch(D, V, dt);
+        }));
+    } else {
+        TRY(run_graphed(L.batch_graph, L, D, dt, diff, nullptr, nullptr, key, [&]() { return dens_diffuse_batch_body(D, dt, diff); }));
+        CU(cudaStreamWaitEvent(L.stream, V.ev, 0));
+        TRY(dens_advect_batch(D, V, dt));
+    }
     // ... and the other dyes' streams and the velocity stream continue after it.
     CU(cudaEventRecord(L.ev, L.stream));
     for (int i = 1; i < n; ++i) CU(cudaStreamWaitEvent(D[i]->stream, L.ev, 0));
