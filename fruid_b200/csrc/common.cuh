@@ -86,14 +86,22 @@ __device__ __forceinline__ float mixf(float a, float b, float t) {
 // kernels of a step (small grids are bound by exactly that).  Every such kernel starts with pdl_enter():
 // wait until the predecessor has completed and its writes are visible (nothing is read or written before),
 // then allow the successor to be scheduled.  Without the launch attribute both instructions are no-ops.
+// The early trigger is taken only while the host-side switch is on (mirrored into this device flag by
+// launch_pdl): with the switch off the kernels must behave exactly like plain stream-ordered launches.
+__device__ int g_pdl_trigger_dev = 0;
 __device__ __forceinline__ void pdl_enter() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (g_pdl_trigger_dev) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 static bool g_pdl_enabled = true;
+static int g_pdl_dev_state = -1;
 template <class... KArgs, class... Args>
 static inline cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                      Args&&... args) {
+    if (g_pdl_dev_state != (int)g_pdl_enabled) {  // first launch, or the switch changed (never inside a capture:
+        const int v = g_pdl_enabled ? 1 : 0;       // a changed switch invalidates the captured graphs first)
+        if (cudaMemcpyToSymbol(g_pdl_trigger_dev, &v, sizeof v) == cudaSuccess) g_pdl_dev_state = v;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
