@@ -42,6 +42,7 @@ SIGNATURES = {
     "fruid_kernel_launch_count": [],
     "fruid_build_info": [],
     "fruid_set_tile_config": [_i, _i, _i],
+    "fruid_debug_tile_plan": [_sz, _sz, _i, _i, _vp],
     "fruid_set_launch_overlap": [_i],
     "fruid_set_graphs_enabled": [_i],
     "fruid_host_register": [_vp, _sz],

@@ -456,6 +456,26 @@ extern "C" int fruid_set_tile_config(int rows_per_warp, int warps, int default_f
     g_cfg_epoch.fetch_add(1);
     return 0;
 }
+// Pure host arithmetic (no CUDA call): the tile shape, fused depth and tiling the library would use for a
+// w x h single-GPU field.  out = {rows per warp, warps, sweeps of the first launch, tiles in x, tiles in y, launches}.
+extern "C" int fruid_debug_tile_plan(size_t w, size_t h, int iters, int fused, int* out) {
+    if (!out) return fail(FRUID_ERR_BAD_ARG, "null out pointer");
+    if (w < 3 || h < 3 || w > (size_t)1 << 20 || h > (size_t)1 << 20) return fail(FRUID_ERR_BAD_SIZE, "grid %zux%zu has no tiling", w, h);
+    if (iters < 2 || (iters & 1)) return fail(FRUID_ERR_ODD_ITERATIONS, "iterations must be even and >= 2, got %d", iters);
+    const Geom g = make_geom(w, h, pitch_for(w));
+    const int T = resolve_fused(g, iters, fused);
+    if (T <= 1) { out[0] = out[1] = 0; out[2] = 1; out[3] = out[4] = 0; out[5] = iters; return 0; }
+    const int nblocks = (iters + T - 1) / T;
+    const int T0 = (iters + nblocks - 1) / nblocks;  // op_lin_solve spreads the sweeps evenly
+    const TileCfg cfg = jacobi_tile_shape(g, T0);
+    if (T0 > jacobi_tile_max_T(cfg.R, cfg.NW)) return fail(FRUID_ERR_BAD_ARG, "fused sweeps T=%d not supported by the current tile config", T0);
+    const int H = T0 + (T0 & 1), TH = cfg.R * cfg.NW;
+    out[0] = cfg.R; out[1] = cfg.NW; out[2] = T0;
+    out[3] = tiles_needed(g.w, 128, 128 - 2 * H);
+    out[4] = tiles_needed(g.h, TH, TH - 2 * H);
+    out[5] = nblocks;
+    return 0;
+}
 extern "C" int fruid_host_register(void* p, size_t bytes) {
     if (!p || !bytes) return fail(FRUID_ERR_BAD_ARG, "null pointer or zero size");
     CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));

@@ -72,6 +72,10 @@ const char *fruid_build_info(void);
  * (128x64, 128x96) and up to 20 sweeps on grids too small to give every SM a tile.  A call pins the
  * shape for every later launch; (0, 0, T) returns to the automatic choice.  Results never change. */
 int fruid_set_tile_config(int rows_per_warp, int warps, int default_fused);
+/* Diagnostics, pure host arithmetic: what the library would use for a w x h single-GPU field and `iters` sweeps
+ * (fused = 0: library choice).  out[6] = {rows per warp, warps, sweeps per launch, tiles in x, tiles in y, launches
+ * per lin_solve}; rows per warp = 0 means one plain kernel per sweep. */
+int fruid_debug_tile_plan(size_t w, size_t h, int iters, int fused, int *out);
 
 /* Tuning knob: replay FluidSim::step / DensitySim::step as captured CUDA graphs (default 1). */
 int fruid_set_graphs_enabled(int on);
