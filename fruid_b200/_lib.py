@@ -12,6 +12,11 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfruid_b200.so")
+# The ordering tests run the same Python layer over the FRUID_DEBUG twin (tail delays, poisoned scratch):
+# FRUID_B200_LIB=debug selects fruid_b200/lib/libfruid_b200_dbg.so.  Nothing else may be selected: there is
+# one product library and no fallback.
+if os.environ.get("FRUID_B200_LIB", "") == "debug":
+    LIB_PATH = os.path.join(_HERE, "lib", "libfruid_b200_dbg.so")
 
 OK = 0
 ERR_BAD_SIZE, ERR_SIZE_MISMATCH, ERR_ODD_ITERATIONS, ERR_CUDA, ERR_NO_PEER, ERR_OOM, ERR_BAD_ARG = range(-1, -8, -1)
@@ -44,6 +49,8 @@ SIGNATURES = {
     "fruid_set_tile_config": [_i, _i, _i],
     "fruid_debug_tile_plan": [_sz, _sz, _i, _i, _vp],
     "fruid_set_launch_overlap": [_i],
+    "fruid_debug_set_schedule": [_i],
+    "fruid_debug_set_tail_delay": [_i],
     "fruid_set_graphs_enabled": [_i],
     "fruid_host_register": [_vp, _sz],
     "fruid_host_unregister": [_vp],

@@ -12,12 +12,16 @@ FluidSim and uses its device-resident velocity instead of uploading it again.
 """
 from __future__ import annotations
 
+import mmap
 import weakref
 
 import numpy as np
 
 from . import _lib
 from ._lib import check, lib, ptr
+
+
+PIN_MIN_BYTES = 64 << 10
 
 
 class Array2D:
@@ -33,21 +37,29 @@ class Array2D:
         # last reference to a FluidSim / DensitySim releases its device memory right away (like Rust's Drop)
         self._owner_ref, self._field = weakref.ref(owner), field
         self._w, self._h = width, height
-        self._host = np.zeros((height, width), np.float32)
-        # page-lock the mirror (fixed length for the object's life) so transfers run at PCIe rate
+        # The mirror owns whole pages (an anonymous mapping, zero-filled like Array2D::new): page-locking it can
+        # then never pin, or later unpin, memory that belongs to another object.  Mirrors below PIN_MIN_BYTES are
+        # not pinned at all -- their transfers are latency-bound either way.
+        nbytes = width * height * 4
+        self._map = mmap.mmap(-1, max(nbytes, 1))
+        self._host = np.frombuffer(self._map, np.float32, width * height).reshape(height, width)
         self._host_ptr = self._host.ctypes.data
-        self._pinned = lib.fruid_host_register(self._host_ptr, self._host.nbytes) == 0
+        self._pinned = nbytes >= PIN_MIN_BYTES and lib.fruid_host_register(self._host_ptr, len(self._map)) == 0
         self._stale = False   # device newer than host
         self._dirty = False   # host newer than device (whole field)
         self._cells = []      # pending single-cell writes (x, y, value)
 
-    def __del__(self):
+    def _release(self):
+        """Unpin; called by the owning simulation BEFORE it destroys its handle (and again, harmlessly, by __del__)."""
         if getattr(self, "_pinned", False) and lib is not None:
             self._pinned = False
             try:
                 lib.fruid_host_unregister(self._host_ptr)
             except Exception:  # interpreter shutdown
                 pass
+
+    def __del__(self):
+        self._release()
 
     @property
     def _owner(self):
@@ -145,6 +157,10 @@ class FluidSim:
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h and lib is not None:
+            lib.fruid_fluid_sync(h)  # nothing may still be reading or writing a mirror
+            for a in (getattr(self, n, None) for n in ("_u", "_v", "_u_prev", "_v_prev")):
+                if a is not None:
+                    a._release()
             lib.fruid_fluid_destroy(h)
 
     # transfers used by the mirrors
@@ -202,6 +218,10 @@ class DensitySim:
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h and lib is not None:
+            lib.fruid_density_sync(h)
+            for a in (getattr(self, n, None) for n in ("_dens", "_dens_prev")):
+                if a is not None:
+                    a._release()
             lib.fruid_density_destroy(h)
 
     def _download(self, field, host):

@@ -88,27 +88,67 @@ __device__ __forceinline__ float mixf(float a, float b, float t) {
 // then allow the successor to be scheduled.  Without the launch attribute both instructions are no-ops.
 // The early trigger is taken only while the host-side switch is on (mirrored into this device flag by
 // launch_pdl): with the switch off the kernels must behave exactly like plain stream-ordered launches.
-__device__ int g_pdl_trigger_dev = 0;
+static __device__ int g_pdl_trigger_dev = 0;
 __device__ __forceinline__ void pdl_enter() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (g_pdl_trigger_dev) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
-static bool g_pdl_enabled = true;
-static int g_pdl_dev_state = -1;
+__device__ __forceinline__ void pdl_enter_arg(int trigger) {  // same, the switch travels as a kernel argument
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// FRUID_DEBUG build (libfruid_b200_dbg.so, used by the ordering tests only): the lowest warps of every block
+// stall for g_dbg_tail_delay_ns before they store their results.  A consumer that starts before its producer
+// has COMPLETED (a missing stream / event / programmatic dependency) then reads stale or poisoned rows
+// deterministically instead of once in a few hundred runs.
+#ifdef FRUID_DEBUG
+static __device__ int g_dbg_tail_delay_ns = 0;
+__device__ __forceinline__ void dbg_tail_delay(int warp_in_block) {
+    if (warp_in_block >= 3) return;
+    const int ns = *(volatile int*)&g_dbg_tail_delay_ns;
+    if (ns <= 0) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < (unsigned long long)ns);
+}
+#else
+__device__ __forceinline__ void dbg_tail_delay(int) {}
+#endif
+
+// ---- host side of the switch -------------------------------------------------------------------------
+// One copy per process (defined in fruid_abi.cu); the kernels' translation units only see the declarations.
+struct PdlState {
+    bool enabled = true;     // fruid_set_launch_overlap / FRUID_B200_LAUNCH_OVERLAP
+    bool unsafe = false;     // FRUID_B200_PDL_UNCHAINED=1: round-1 behaviour (attribute on every launch), experiments only
+};
+extern PdlState g_pdl;
+// Programmatic launch CHAINS.  The attribute is only put on a kernel whose immediate predecessor on the same
+// stream is a kernel this thread launched in the same API call: after anything else -- a cudaGraphLaunch, an
+// event wait, a copy, the previous API call's work -- the launch is a plain, fully stream-ordered one.  (The
+// round-1 library attributed every launch.  Its opt-in density/velocity overlap launched a PDL advect straight
+// after a replayed graph and an event wait and showed an intermittent stale read)
+bool pdl_chain_continue(cudaStream_t st);  // true: the previous operation on st was a kernel of this chain; marks st open
+void pdl_chain_break(cudaStream_t st);     // a non-kernel operation was enqueued on st
+void pdl_chain_reset();                    // a new API call begins: nothing is chained across calls
+int pdl_dev_flag_sync(int* dev_state, const void* symbol);  // mirrors g_pdl.enabled into a __device__ flag
+
 template <class... KArgs, class... Args>
 static inline cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                      Args&&... args) {
-    if (g_pdl_dev_state != (int)g_pdl_enabled) {  // first launch, or the switch changed (never inside a capture:
-        const int v = g_pdl_enabled ? 1 : 0;       // a changed switch invalidates the captured graphs first)
-        if (cudaMemcpyToSymbol(g_pdl_trigger_dev, &v, sizeof v) == cudaSuccess) g_pdl_dev_state = v;
-    }
+    static int dev_state = -1;  // per translation unit, like g_pdl_trigger_dev
+    if (dev_state != (int)g_pdl.enabled) pdl_dev_flag_sync(&dev_state, (const void*)&g_pdl_trigger_dev);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = (pdl && g_pdl_enabled) ? 1 : 0;
+    const bool chained = pdl_chain_continue(st);
+    cfg.numAttrs = (pdl && g_pdl.enabled && (chained || g_pdl.unsafe)) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 

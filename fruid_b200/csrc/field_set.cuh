@@ -37,7 +37,7 @@ struct StepGraph {
     int iters = 0, fused = 0;
     const void* a0 = nullptr;      // density: the velocity pointers the graph was captured with
     const void* a1 = nullptr;
-    std::vector<const void*> extra;  // batched dye step: the participating handles
+    std::vector<uint64_t> extra;   // unique ids (FieldSet::uid) of every handle whose buffers the graph bakes in
     uint64_t kernels = 0;          // kernel launches inside the graph
     int cfg_epoch = -1;            // value of g_cfg_epoch the parameters were recorded under
     bool failed = false;           // capture did not work for these parameters: stay on direct launches
@@ -50,8 +50,12 @@ struct StepGraph {
     }
 };
 static bool g_graphs_enabled = true;
+// Process-unique handle ids: a graph remembers the ids (not the host addresses) of the handles it was captured
+// with, so a handle that malloc places at the address of a destroyed one can never replay the dead handle's graph.
+static std::atomic<uint64_t> g_next_uid{1};
 
 struct FieldSet {
+    uint64_t uid = g_next_uid.fetch_add(1);
     StepGraph graph;
     StepGraph batch_graph;                       // fruid_density_step_dev_batch led by this handle
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // fork / join of the batched step (also inside captures)
@@ -89,7 +93,7 @@ struct FieldSet {
     std::vector<cudaEvent_t> readers;
     int wait_readers() {
         TRY(quiesce_gathers());
-        for (cudaEvent_t e : readers) CU(cudaStreamWaitEvent(stream, e, 0));
+        for (cudaEvent_t e : readers) CU(stream_wait(stream, e));
         readers.clear();
         return 0;
     }
@@ -212,7 +216,7 @@ struct FieldSet {
             CU(cudaEventCreateWithFlags(&up_ev[field], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&up_used[field], cudaEventDisableTiming));
         } else {
-            CU(cudaStreamWaitEvent(copy_stream, up_used[field], 0));  // previous staged upload has been consumed
+            CU(stream_wait(copy_stream, up_used[field]));  // previous staged upload has been consumed
         }
         CU(cudaMemcpy2DAsync(up_stage[field], g.pitch * sizeof(float), host, (size_t)g.w * sizeof(float),
                              (size_t)g.w * sizeof(float), rows, cudaMemcpyHostToDevice, copy_stream));
@@ -225,7 +229,7 @@ struct FieldSet {
         for (int f = 0; f < 4; ++f) {
             if (!up_pending[f]) continue;
             TRY(wait_readers());
-            CU(cudaStreamWaitEvent(stream, up_ev[f], 0));
+            CU(stream_wait(stream, up_ev[f]));
             const size_t rows = (size_t)(own_hi() - own_lo());
             CU(cudaMemcpyAsync(buf[f] + (size_t)own_lo() * g.pitch, up_stage[f], g.pitch * rows * sizeof(float),
                                cudaMemcpyDeviceToDevice, stream));
@@ -245,12 +249,12 @@ struct FieldSet {
             CU(cudaEventCreateWithFlags(&dl_snap, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&dl_done, cudaEventDisableTiming));
         } else {
-            CU(cudaStreamWaitEvent(stream, dl_done, 0));  // previous download has left the snapshot buffer
+            CU(stream_wait(stream, dl_done));  // previous download has left the snapshot buffer
         }
         CU(cudaMemcpyAsync(dl_stage, buf[field] + (size_t)own_lo() * g.pitch, g.pitch * rows * sizeof(float),
                            cudaMemcpyDeviceToDevice, stream));
         CU(cudaEventRecord(dl_snap, stream));
-        CU(cudaStreamWaitEvent(copy_stream, dl_snap, 0));
+        CU(stream_wait(copy_stream, dl_snap));
         CU(cudaMemcpy2DAsync(host, (size_t)g.w * sizeof(float), dl_stage, g.pitch * sizeof(float), (size_t)g.w * sizeof(float),
                              rows, cudaMemcpyDeviceToHost, copy_stream));
         CU(cudaEventRecord(dl_done, copy_stream));
@@ -419,7 +423,7 @@ struct fruid_density { FieldSet s; };  // buf: 0=dens 1=dens_prev 2=scratch (lib
 // lin_solve), because the graph bakes the pointers in.
 template <class Body>
 static int run_graphed(StepGraph& G, FieldSet& S, const std::vector<FieldSet*>& parts, float dt, float p, const void* a0,
-                       const void* a1, const std::vector<const void*>& extra, Body body) {
+                       const void* a1, const std::vector<uint64_t>& extra, Body body) {
     bool usable = g_graphs_enabled && !g_prof_on;
     for (FieldSet* P : parts) usable &= !P->is_slab();
     if (!usable) return body();
@@ -433,6 +437,8 @@ static int run_graphed(StepGraph& G, FieldSet& S, const std::vector<FieldSet*>& 
     }
     if (G.exec) {
         CU(cudaGraphLaunch(G.exec, S.stream));
+        pdl_chain_break(S.stream);
+        for (FieldSet* P : parts) { pdl_chain_break(P->stream); if (P->stream2) pdl_chain_break(P->stream2); }
         g_launches.fetch_add(G.kernels, std::memory_order_relaxed);
         return 0;
     }
@@ -465,10 +471,12 @@ static int run_graphed(StepGraph& G, FieldSet& S, const std::vector<FieldSet*>& 
     cudaGraphDestroy(graph);
     G.kernels = nk;
     CU(cudaGraphLaunch(G.exec, S.stream));
+    pdl_chain_break(S.stream);
+    for (FieldSet* P : parts) { pdl_chain_break(P->stream); if (P->stream2) pdl_chain_break(P->stream2); }
     g_launches.fetch_add(nk, std::memory_order_relaxed);
     return 0;
 }
 template <class Body>
-static int run_step_graphed(FieldSet& S, float dt, float p, const void* a0, const void* a1, Body body) {
-    return run_graphed(S.graph, S, {&S}, dt, p, a0, a1, {}, body);
+static int run_step_graphed(FieldSet& S, float dt, float p, const void* a0, const void* a1, Body body, uint64_t vel_uid = 0) {
+    return run_graphed(S.graph, S, {&S}, dt, p, a0, a1, {S.uid, vel_uid}, body);
 }

@@ -52,30 +52,88 @@ extern "C" int fruid_profile_report(fruid_kernel_stat* out, size_t cap, size_t* 
 
 extern "C" const char* fruid_last_error(void) { return g_err; }
 extern "C" uint64_t fruid_kernel_launch_count(void) { return g_launches.load(); }
-extern "C" const char* fruid_build_info(void) { return "fruid_b200 0.1 (sm_100a, -fmad=false, IEEE f32 rn)"; }
+extern "C" const char* fruid_build_info(void) {
+#ifdef FRUID_DEBUG
+    return "fruid_b200 0.2 (sm_100a, -fmad=false, IEEE f32 rn) FRUID_DEBUG";
+#else
+    return "fruid_b200 0.2 (sm_100a, -fmad=false, IEEE f32 rn)";
+#endif
+}
 
-// Tuning / debugging knob: replay steps as CUDA graphs (default on).
-// Tuning / debugging knob: programmatic dependent launch between the kernels of a step (default on).
 static bool g_vel_fork = true;      // u and v diffuse on two streams
-// Density add_source + diffuse beside the velocity step still in flight (only the advect waits for u, v).  OFF by
-// default: with it the advect is launched directly after the replayed diffuse graph, and with that sequence the
-// test suite showed an intermittent mismatch (about 1 suite run in 12, rows 0-3 of one density field) that was not
-// tracked down; FRUID_B200_DENS_OVERLAP=1 turns it on (250^2 scene step 85 -> 70 us, 4096^2 1.15 -> 1.135 ms).
+// Density add_source + diffuse beside the velocity step still in flight (only the advect waits for u, v).
+// FRUID_B200_DENS_OVERLAP=1 / fruid_debug_set_schedule turn it on; default: one captured graph of the whole density step
+// after the velocity step.
 static bool g_dens_overlap = false;
+
+// ---- programmatic launch chains (declared in common.cuh) ------------------------------------------------
+namespace fruid {
+PdlState g_pdl;
+namespace {
+struct ChainSlot { cudaStream_t st; bool open; };
+thread_local ChainSlot t_chain[16];
+thread_local int t_chain_n = 0;
+}  // namespace
+bool pdl_chain_continue(cudaStream_t st) {
+    for (int i = 0; i < t_chain_n; ++i)
+        if (t_chain[i].st == st) { const bool was = t_chain[i].open; t_chain[i].open = true; return was; }
+    if (t_chain_n < 16) t_chain[t_chain_n++] = ChainSlot{st, true};
+    return false;  // (more than 16 streams in one call: the extra ones simply never chain)
+}
+void pdl_chain_break(cudaStream_t st) {
+    for (int i = 0; i < t_chain_n; ++i)
+        if (t_chain[i].st == st) { t_chain[i].open = false; return; }
+}
+void pdl_chain_reset() { t_chain_n = 0; }
+int pdl_dev_flag_sync(int* dev_state, const void* symbol) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    const int v = g_pdl.enabled ? 1 : 0;
+    // every device this process has a context on reads its own copy of the flag
+    int ndev = 0, cur = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cudaGetDevice(&cur) != cudaSuccess) return -1;
+    (void)ndev;
+    if (cudaMemcpyToSymbol(symbol, &v, sizeof v) != cudaSuccess) { cudaGetLastError(); return -1; }
+    *dev_state = v;
+    return 0;
+}
+}  // namespace fruid
+
 namespace { struct PdlEnv { PdlEnv() {
-    if (const char* e = getenv("FRUID_B200_LAUNCH_OVERLAP")) g_pdl_enabled = atoi(e) != 0;
+    if (const char* e = getenv("FRUID_B200_LAUNCH_OVERLAP")) g_pdl.enabled = atoi(e) != 0;
+    if (const char* e = getenv("FRUID_B200_PDL_UNCHAINED")) g_pdl.unsafe = atoi(e) != 0;
     if (const char* e = getenv("FRUID_B200_VEL_FORK")) g_vel_fork = atoi(e) != 0;
     if (const char* e = getenv("FRUID_B200_DENS_OVERLAP")) g_dens_overlap = atoi(e) != 0;
 } } g_pdl_env; }
-extern "C" int fruid_set_launch_overlap(int on) { g_pdl_enabled = on != 0; g_cfg_epoch.fetch_add(1); return 0; }
+// Tuning / debugging knob: programmatic dependent launch between the kernels of a step (default on).
+extern "C" int fruid_set_launch_overlap(int on) { g_pdl.enabled = on != 0; g_cfg_epoch.fetch_add(1); return 0; }
+// Tuning / debugging knob: replay steps as CUDA graphs (default on).
 extern "C" int fruid_set_graphs_enabled(int on) { g_graphs_enabled = on != 0; g_cfg_epoch.fetch_add(1); return 0; }
+// Debug knobs of the ordering tests.  bit 0: density diffuse beside the velocity step (default on), bit 1: u / v
+// diffuse fork (default on), bit 2: round-1 launch attribution (programmatic attribute on EVERY launch; unsafe).
+extern "C" int fruid_debug_set_schedule(int mask) {
+    g_dens_overlap = (mask & 1) != 0; g_vel_fork = (mask & 2) != 0; g_pdl.unsafe = (mask & 4) != 0;
+    g_cfg_epoch.fetch_add(1);
+    return 0;
+}
+// FRUID_DEBUG builds: the lowest warps of every block wait `ns` before storing (0 = off).  Release builds: no-op, returns 1.
+extern "C" int fruid_debug_set_tail_delay(int ns) {
+#ifdef FRUID_DEBUG
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyToSymbol(g_dbg_tail_delay_ns, &ns, sizeof ns));
+    return 0;
+#else
+    (void)ns;
+    return 1;
+#endif
+}
 
 // Live single-process registry of velocity handles: fruid_density_step_host looks its (u, v) pointers up here.
 static std::mutex g_fluids_mu;
 static std::vector<fruid_fluid*> g_fluids;
 static std::atomic<uint64_t> g_velocity_uploads{0};
 
-#define NEED(h) do { if (!(h)) return fail(FRUID_ERR_BAD_ARG, "null handle"); CU(cudaSetDevice((h)->s.device)); } while (0)
+#define NEED(h) do { if (!(h)) return fail(FRUID_ERR_BAD_ARG, "null handle"); pdl_chain_reset(); CU(cudaSetDevice((h)->s.device)); } while (0)
 
 extern "C" int fruid_fluid_create(size_t w, size_t h, fruid_fluid_t** out) {
     if (!out) return fail(FRUID_ERR_BAD_ARG, "null out pointer");
@@ -247,15 +305,15 @@ extern "C" int fruid_density_step_dev(fruid_density_t* d, fruid_fluid_t* vel, fl
     if (s.is_slab()) {
         TRY(op_dens_step_slab(s, vs.buf[0], vs.buf[1], diff, dt, vs.ev));
     } else if (!g_dens_overlap) {  // the whole step is one captured graph, after the velocity step
-        CU(cudaStreamWaitEvent(s.stream, vs.ev, 0));
+        CU(stream_wait(s.stream, vs.ev));
         TRY(run_step_graphed(s, dt, diff, vs.buf[0], vs.buf[1], [&]() {
             return op_dens_step(s.buf[0], s.buf[1], vs.buf[0], vs.buf[1], s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream);
-        }));
+        }, vs.uid));
     } else {
         TRY(run_step_graphed(s, dt, diff, nullptr, nullptr, [&]() {
             return op_add_source_diffuse(B_POSITIVE, s.buf[1], s.buf[0], s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream);
         }));
-        CU(cudaStreamWaitEvent(s.stream, vs.ev, 0));
+        CU(stream_wait(s.stream, vs.ev));
         float* dd[1] = {s.buf[0]};
         const float* d0[1] = {s.buf[1]};
         const int b[1] = {B_POSITIVE};
@@ -265,7 +323,7 @@ extern "C" int fruid_density_step_dev(fruid_density_t* d, fruid_fluid_t* vel, fl
     if (s.is_slab()) {
         if (std::find(vs.readers.begin(), vs.readers.end(), s.ev) == vs.readers.end()) vs.readers.push_back(s.ev);
     } else {
-        CU(cudaStreamWaitEvent(vs.stream, s.ev, 0));
+        CU(stream_wait(vs.stream, s.ev));
     }
     return 0;
 }
@@ -278,11 +336,11 @@ static int dens_diffuse_batch_body(const std::vector<FieldSet*>& D, float dt, fl
     CU(cudaEventRecord(L.ev_fork, L.stream));
     for (size_t i = 0; i < D.size(); ++i) {
         FieldSet& s = *D[i];
-        if (i) CU(cudaStreamWaitEvent(s.stream, L.ev_fork, 0));
+        if (i) CU(stream_wait(s.stream, L.ev_fork));
         TRY(op_add_source_diffuse(B_POSITIVE, s.buf[1], s.buf[0], s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream));  // lib.rs:172,175
         if (i) {
             CU(cudaEventRecord(s.ev_join, s.stream));
-            CU(cudaStreamWaitEvent(L.stream, s.ev_join, 0));
+            CU(stream_wait(L.stream, s.ev_join));
         }
     }
     return 0;
@@ -308,6 +366,7 @@ extern "C" int fruid_density_step_dev_batch(fruid_density_t* const* dyes, int n,
         for (int k = 0; k < i; ++k)
             if (dyes[k] == dyes[i]) return fail(FRUID_ERR_BAD_ARG, "dye %d given twice", i);
     }
+    pdl_chain_reset();
     FieldSet& L = dyes[0]->s;
     FieldSet& V = vel->s;
     bool batchable = !L.is_slab() && !V.is_slab() && n > 1;
@@ -318,7 +377,7 @@ extern "C" int fruid_density_step_dev_batch(fruid_density_t* const* dyes, int n,
     }
     CU(cudaSetDevice(L.device));
     std::vector<FieldSet*> D;
-    std::vector<const void*> key;
+    std::vector<uint64_t> key{V.uid};
     for (int i = 0; i < n; ++i) {
         FieldSet& s = dyes[i]->s;
         if (V.g.w != s.g.w || V.g.gh != s.g.gh)
@@ -326,7 +385,7 @@ extern "C" int fruid_density_step_dev_batch(fruid_density_t* const* dyes, int n,
         if (s.device != V.device) return fail(FRUID_ERR_BAD_ARG, "density and velocity live on different devices");
         TRY(s.consume_uploads());
         D.push_back(&s);
-        key.push_back(&s);
+        key.push_back(s.uid);
     }
     // Everything is driven from the first dye's stream: it waits for whatever is still queued on the other dyes'
     // streams (uploads, injects, fills), runs the diffuses (beside the velocity step still in flight: only the
@@ -334,23 +393,23 @@ extern "C" int fruid_density_step_dev_batch(fruid_density_t* const* dyes, int n,
     CU(cudaEventRecord(V.ev, V.stream));
     for (int i = 1; i < n; ++i) {
         CU(cudaEventRecord(D[i]->ev, D[i]->stream));
-        CU(cudaStreamWaitEvent(L.stream, D[i]->ev, 0));
+        CU(stream_wait(L.stream, D[i]->ev));
     }
     if (!g_dens_overlap) {  // one captured graph: fork, diffuses, join, advect -- after the velocity step
-        CU(cudaStreamWaitEvent(L.stream, V.ev, 0));
+        CU(stream_wait(L.stream, V.ev));
         TRY(run_graphed(L.batch_graph, L, D, dt, diff, V.buf[0], V.buf[1], key, [&]() {
             TRY(dens_diffuse_batch_body(D, dt, diff));
             return dens_advect_batch(D, V, dt);
         }));
     } else {
         TRY(run_graphed(L.batch_graph, L, D, dt, diff, nullptr, nullptr, key, [&]() { return dens_diffuse_batch_body(D, dt, diff); }));
-        CU(cudaStreamWaitEvent(L.stream, V.ev, 0));
+        CU(stream_wait(L.stream, V.ev));
         TRY(dens_advect_batch(D, V, dt));
     }
     // ... and the other dyes' streams and the velocity stream continue after it.
     CU(cudaEventRecord(L.ev, L.stream));
-    for (int i = 1; i < n; ++i) CU(cudaStreamWaitEvent(D[i]->stream, L.ev, 0));
-    CU(cudaStreamWaitEvent(V.stream, L.ev, 0));
+    for (int i = 1; i < n; ++i) CU(stream_wait(D[i]->stream, L.ev));
+    CU(stream_wait(V.stream, L.ev));
     return 0;
 }
 extern "C" int fruid_density_step_host(fruid_density_t* d, const float* u, const float* v, float dt, float diff) {
@@ -403,7 +462,7 @@ static int draw_density_impl(fruid_density_t* c, fruid_density_t* m, fruid_densi
     }
     for (int i = 1; i < 4; ++i) {  // the other dyes' steps must have finished before we read them
         CU(cudaEventRecord(all[i]->s.ev, all[i]->s.stream));
-        CU(cudaStreamWaitEvent(S.stream, all[i]->s.ev, 0));
+        CU(stream_wait(S.stream, all[i]->s.ev));
     }
     const size_t per_cell = verts ? 24 : 3;
     const size_t bytes = (size_t)S.g.w * S.g.h * per_cell * sizeof(float);
@@ -478,12 +537,20 @@ extern "C" int fruid_debug_tile_plan(size_t w, size_t h, int iters, int fused, i
 }
 extern "C" int fruid_host_register(void* p, size_t bytes) {
     if (!p || !bytes) return fail(FRUID_ERR_BAD_ARG, "null pointer or zero size");
-    CU(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();  // callers treat pinning as best effort: do not leave a sticky error for the next launch check
+        return fail(FRUID_ERR_CUDA, "cudaHostRegister(%p, %zu) failed: %s", p, bytes, cudaGetErrorString(e));
+    }
     return 0;
 }
 extern "C" int fruid_host_unregister(void* p) {
     if (!p) return fail(FRUID_ERR_BAD_ARG, "null pointer");
-    CU(cudaHostUnregister(p));
+    const cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(FRUID_ERR_CUDA, "cudaHostUnregister(%p) failed: %s", p, cudaGetErrorString(e));
+    }
     return 0;
 }
 
@@ -496,6 +563,7 @@ struct Scratch {  // a few temporary device fields for one operator call
     std::vector<float*> bufs;
     ~Scratch() { for (float* p : bufs) cudaFree(p); }
     int init(size_t w, size_t h) {
+        pdl_chain_reset();
         if (w < 2 || h < 2) return fail(FRUID_ERR_BAD_SIZE, "grid must be at least 2x2 (got %zux%zu)", w, h);
         g = make_geom(w, h, pitch_for(w));
         return 0;
@@ -587,6 +655,7 @@ extern "C" int fruid_op_project(float* u, float* v, float* p, float* div, float*
 // device-pointer variants
 // --------------------------------------------------------------------------------------
 static int check_dev_layout(const void* p, size_t w, size_t h, size_t pitch) {
+    pdl_chain_reset();
     if (w < 2 || h < 2) return fail(FRUID_ERR_BAD_SIZE, "grid must be at least 2x2");
     if (pitch < w || (pitch & 3) || ((uintptr_t)p & 15)) return fail(FRUID_ERR_BAD_ARG, "pitch must be >= w and a multiple of 4 floats; base 16-byte aligned");
     return 0;

@@ -58,8 +58,15 @@ static inline void prof_pre(cudaStream_t st) {
     cudaEventRecord(r.e0, st);
     g_prof.push_back(r);
 }
+// cudaStreamWaitEvent + the bookkeeping of programmatic launch chains (common.cuh): the next kernel on `st` has a
+// dependency that is not its predecessor kernel, so it is launched without the programmatic attribute.
+static inline cudaError_t stream_wait(cudaStream_t st, cudaEvent_t ev) {
+    pdl_chain_break(st);
+    return cudaStreamWaitEvent(st, ev, 0);
+}
 static inline int launched(const char* what, cudaStream_t st) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    (void)pdl_chain_continue(st);  // a kernel is now the newest operation on st (plain <<<>>> launches pass here too)
     if (g_prof_on) {
         std::lock_guard<std::mutex> lk(g_prof_mu);
         if (!g_prof.empty() && g_prof.back().name == nullptr) {

@@ -73,6 +73,7 @@ __global__ void k_add_source4(float* __restrict__ x1, const float* __restrict__ 
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     float4* X1 = reinterpret_cast<float4*>(x1);
+    dbg_tail_delay(threadIdx.x >> 5);
     const float4 a = X1[i], s = ld4(s1 + 4 * i);
     X1[i] = make_float4(fadd(a.x, fmul(s.x, dt)), fadd(a.y, fmul(s.y, dt)), fadd(a.z, fmul(s.z, dt)), fadd(a.w, fmul(s.w, dt)));
     if (x2) {
@@ -106,6 +107,7 @@ __global__ void k_divergence4(float* __restrict__ div, float* __restrict__ p, co
     d.y = fadd(fadd(0.0f, fmul(sx, fsub(uc.z, uc.x))), fmul(sy, fsub(vd.y, vu.y)));
     d.z = fadd(fadd(0.0f, fmul(sx, fsub(uc.w, uc.y))), fmul(sy, fsub(vd.z, vu.z)));
     d.w = fadd(fadd(0.0f, fmul(sx, fsub(ur, uc.z))), fmul(sy, fsub(vd.w, vu.w)));
+    dbg_tail_delay(threadIdx.y);
     store_row4_bnd(div, g, B_POSITIVE, gx0, gy, d);
     if (p) store_row4_bnd(p, g, B_POSITIVE, gx0, gy, make_float4(0.f, 0.f, 0.f, 0.f));
 }
@@ -132,6 +134,7 @@ __global__ void k_gradient4(float* __restrict__ u, float* __restrict__ v, const 
     vn.y = fadd(vo.y, fmul(gys, fsub(pd.y, pu.y)));
     vn.z = fadd(vo.z, fmul(gys, fsub(pd.z, pu.z)));
     vn.w = fadd(vo.w, fmul(gys, fsub(pd.w, pu.w)));
+    dbg_tail_delay(threadIdx.y);
     store_row4_bnd(u, g, B_NEGX, gx0, gy, un);
     store_row4_bnd(v, g, B_NEGY, gx0, gy, vn);
 }
@@ -232,6 +235,7 @@ __device__ __forceinline__ void advect4_block(const AdvectArgs& a, const float* 
                 if (r < tab.me - 1 || r > tab.me + 1) spin_until(&tab.src_done[r], tab.event, tab.error);
         }
     }
+    dbg_tail_delay(threadIdx.y);
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
         float4 r;

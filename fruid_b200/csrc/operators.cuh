@@ -74,6 +74,13 @@ static int op_lin_solve(int b, float*& x, const float* x0, float*& scratch, cons
     }
     const int nblocks = (iters + fused - 1) / fused;
     int done = 0;
+#ifdef FRUID_DEBUG
+    // scratch and the add_source temporary are write-before-read (lib.rs:65,68): fill them with NaNs so that a
+    // launch that reads them before its producer has finished yields NaNs instead of plausible stale values
+    CU(cudaMemsetAsync(scratch, 0xFF, g.pitch * (size_t)g.h * sizeof(float), st));
+    if (fuse_src && nblocks > 1 && z_tmp && !slab) CU(cudaMemsetAsync(z_tmp, 0xFF, g.pitch * (size_t)g.h * sizeof(float), st));
+    pdl_chain_break(st);
+#endif
     for (int k = 0; k < nblocks; ++k) {
         const int T = (iters - done + (nblocks - k) - 1) / (nblocks - k);  // spread evenly
         const bool fs = fuse_src && k == 0;  // first block also performs add_source(x0, x, dt) -> z_tmp
@@ -201,11 +208,11 @@ static int op_vel_step(float*& u, float*& v, float*& u0, float*& v0, float*& s, 
                        float dt, int iters, int fused, cudaStream_t st, VelFork* fk = nullptr) {
     if (fk) {
         CU(cudaEventRecord(fk->fork, st));
-        CU(cudaStreamWaitEvent(fk->st2, fk->fork, 0));
+        CU(stream_wait(fk->st2, fk->fork));
         TRY(op_add_source_diffuse(B_NEGY, v0, v, fk->scratch_v, fk->tmp_v, g, visc, dt, iters, fused, fk->st2));  // lib.rs:191,197
         CU(cudaEventRecord(fk->join, fk->st2));
         TRY(op_add_source_diffuse(B_NEGX, u0, u, s, s2, g, visc, dt, iters, fused, st));                          // lib.rs:190,194
-        CU(cudaStreamWaitEvent(st, fk->join, 0));
+        CU(stream_wait(st, fk->join));
     } else {
         TRY(op_add_source_diffuse(B_NEGX, u0, u, s, s2, g, visc, dt, iters, fused, st));  // lib.rs:190,194
         TRY(op_add_source_diffuse(B_NEGY, v0, v, s, s2, g, visc, dt, iters, fused, st));  // lib.rs:191,197

@@ -74,7 +74,7 @@ static int op_dens_step_slab(FieldSet& S, const float* u, const float* v, float 
     SlabSolve sd{SLAB_HALO, SLAB_HALO, 0, [&S](std::initializer_list<float*> f) { return S.exchange(f); }};
     TRY(op_lin_solve(B_POSITIVE, x0, x, s, g, a, c, S.iters, T, st, false, true, dt, s2, &sd));  // lib.rs:172,175
     S.slab.ev_adv += 1;                        // advect pass 1 broadcasts "my x0 is final"
-    CU(cudaStreamWaitEvent(st, vel_ready, 0)); // u, v of this step
+    CU(stream_wait(st, vel_ready)); // u, v of this step
     SlabTable tab{};
     TRY(S.fill_table(tab, 0, x0));
     float* d[1] = {x};

@@ -18,8 +18,10 @@
  *     fruid_last_error() gives a thread-local message for the last failure.
  *     The reference API is infallible (misuse panics); a shim panics on != 0.
  *   - A handle is not thread-safe; distinct handles may be used from distinct
- *     threads.  Work is enqueued on the handle's CUDA stream; download/sync
- *     calls block until the data is on the host.
+ *     threads (library-global state -- caches, tuning knobs -- is mutex-guarded;
+ *     the fruid_set_* / fruid_debug_* knobs are process-wide and meant to be set
+ *     while no step is in flight).  Work is enqueued on the handle's CUDA stream;
+ *     download/sync calls block until the data is on the host.
  *   - There is no CPU fallback: without a CUDA device every call fails with
  *     FRUID_ERR_CUDA.
  */
@@ -83,6 +85,15 @@ int fruid_set_graphs_enabled(int on);
  * (programmatic dependent launch; each kernel first waits for the predecessor's completion, so results
  * cannot change).  Default on (environment FRUID_B200_LAUNCH_OVERLAP=0 turns it off at load). */
 int fruid_set_launch_overlap(int on);
+
+/* Debug knobs of the ordering tests (tests/test_ordering_gpu.py).  fruid_debug_set_schedule: bit 0 = density
+ * add_source + diffuse beside the velocity step still in flight, bit 1 = u / v diffuse on two streams, bit 2 = the
+ * round-1 launch attribution (programmatic attribute on every launch, even straight after a graph launch or an
+ * event wait; kept only to reproduce the stale read it caused).  fruid_debug_set_tail_delay: in the FRUID_DEBUG build
+ * (libfruid_b200_dbg.so) the lowest warps of every block wait `ns` nanoseconds before they store, which turns a
+ * missing dependency into a deterministic mismatch; the release build ignores it and returns 1. */
+int fruid_debug_set_schedule(int mask);
+int fruid_debug_set_tail_delay(int ns);
 
 /* Page-lock / unlock a caller-owned host array (e.g. the Vec<f32> inside an Array2D). */
 int fruid_host_register(void *p, size_t bytes);

@@ -52,10 +52,10 @@ def rand_field(rng, w, h, scale=1.0):
     return (rng.standard_normal((h, w)) * scale).astype(np.float32)
 
 
-@pytest.fixture(autouse=True)
-def _release_device_objects():
-    """Handles own device memory, streams and captured graphs: drop whatever a test left behind before the
-    next one starts, so that a test never runs concurrently with the teardown of its predecessor's objects."""
-    yield
-    import gc
-    gc.collect()
+@pytest.fixture(scope="session")
+def fb():
+    """The product package over libfruid_b200.so (built in-tree; raises if the library is missing)."""
+    import __graft_entry__
+    __graft_entry__.build()
+    import fruid_b200
+    return fruid_b200

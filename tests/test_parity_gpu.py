@@ -21,14 +21,6 @@ FUSED = [1, 0]  # one sweep per launch, and the library default (fused register-
 
 
 @pytest.fixture(scope="module")
-def fb():
-    import __graft_entry__
-    __graft_entry__.build()
-    import fruid_b200
-    return fruid_b200
-
-
-@pytest.fixture(scope="module")
 def O(oracle_mod):
     return oracle_mod.lib(True)
 
