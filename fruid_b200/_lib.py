@@ -38,8 +38,27 @@ if not os.path.exists(LIB_PATH):
 
 lib = ctypes.CDLL(LIB_PATH)
 
-_sz, _f, _i, _vp = ctypes.c_size_t, ctypes.c_float, ctypes.c_int, ctypes.c_void_p
+_sz, _f, _i = ctypes.c_size_t, ctypes.c_float, ctypes.c_int
 _fp = ctypes.POINTER(ctypes.c_float)
+
+
+class _vp(ctypes.c_void_p):
+    """void* parameter that also takes a numpy array DIRECTLY: `lib.fruid_fluid_upload(h, f, array)`.
+
+    Passing the array itself (rather than `ptr(array)`, an integer) keeps it referenced by the call's argument
+    tuple for the duration of the call.  `ptr(np.ascontiguousarray(x))` on a temporary does not: the temporary dies
+    when ptr() returns and the library is handed the address of freed memory -- the cause of the "intermittent
+    mismatch" that round 1 chased in the kernels (DESIGN.md 4.3)."""
+
+    @classmethod
+    def from_param(cls, obj):
+        if isinstance(obj, np.ndarray):
+            if obj.dtype != np.float32 or not obj.flags.c_contiguous:
+                raise TypeError("expected a C-contiguous float32 array")
+            return ctypes.c_void_p(obj.ctypes.data)
+        if obj is None or isinstance(obj, int):
+            return ctypes.c_void_p(obj)
+        return obj  # ctypes instances: handles, arrays of handles, byref(...)
 
 # name -> argtypes; every function returns int unless listed in _RESTYPES.
 SIGNATURES = {
@@ -51,6 +70,7 @@ SIGNATURES = {
     "fruid_set_launch_overlap": [_i],
     "fruid_debug_set_schedule": [_i],
     "fruid_debug_set_tail_delay": [_i],
+    "fruid_debug_recip_mode": [_f, _vp, _vp],
     "fruid_set_graphs_enabled": [_i],
     "fruid_host_register": [_vp, _sz],
     "fruid_host_unregister": [_vp],
@@ -78,6 +98,7 @@ SIGNATURES = {
     "fruid_density_upload_async": [_vp, _i, _vp],
     "fruid_density_download_async": [_vp, _i, _vp],
     "fruid_fluid_inject": [_vp, _i, _sz, _sz, _f],
+    "fruid_fluid_fill": [_vp, _i, _f],
     "fruid_fluid_set_iterations": [_vp, _i],
     "fruid_fluid_set_fused_sweeps": [_vp, _i],
     "fruid_fluid_step": [_vp, _f, _f],
@@ -114,8 +135,8 @@ _RESTYPES = {
     "fruid_build_info": ctypes.c_char_p,
     "fruid_kernel_launch_count": ctypes.c_uint64,
     "fruid_host_velocity_uploads": ctypes.c_uint64,
-    "fruid_fluid_stream": _vp,
-    "fruid_density_stream": _vp,
+    "fruid_fluid_stream": ctypes.c_void_p,
+    "fruid_density_stream": ctypes.c_void_p,
     "fruid_fluid_width": _sz,
     "fruid_fluid_height": _sz,
 }
@@ -131,7 +152,8 @@ def check(code: int) -> None:
 
 
 def ptr(a: np.ndarray) -> int:
-    """Address of a C-contiguous float32 array (kept alive by the caller)."""
+    """Address of a C-contiguous float32 array.  The CALLER must keep `a` referenced until the library call that
+    uses the address has returned: never call this on a temporary (pass the array itself instead, see _vp)."""
     if a.dtype != np.float32 or not a.flags.c_contiguous:
         raise TypeError("expected a C-contiguous float32 array")
     return a.ctypes.data

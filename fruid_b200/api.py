@@ -47,7 +47,8 @@ class Array2D:
         self._pinned = nbytes >= PIN_MIN_BYTES and lib.fruid_host_register(self._host_ptr, len(self._map)) == 0
         self._stale = False   # device newer than host
         self._dirty = False   # host newer than device (whole field)
-        self._cells = []      # pending single-cell writes (x, y, value)
+        self._fill = None     # pending whole-field fill value (performed on the device, nothing uploaded)
+        self._cells = []      # pending single-cell writes (x, y, value), applied after the fill
 
     def _release(self):
         """Unpin; called by the owning simulation BEFORE it destroys its handle (and again, harmlessly, by __del__)."""
@@ -87,13 +88,16 @@ class Array2D:
         if self._dirty:
             self._owner._upload(self._field, self._host)
         else:
+            if self._fill is not None:
+                self._owner._fill_dev(self._field, self._fill)
             for (x, y, val) in self._cells:
                 self._owner._inject(self._field, x, y, val)
         self._dirty = False
+        self._fill = None
         self._cells = []
 
     def _mark_stale(self):
-        self._stale, self._dirty, self._cells = True, False, []
+        self._stale, self._dirty, self._fill, self._cells = True, False, None, []
 
     # -- Rust-like surface --------------------------------------------------------
     def data(self) -> np.ndarray:
@@ -110,14 +114,14 @@ class Array2D:
         return self._host.reshape(-1)
 
     def fill(self, val: float) -> None:
-        """`data_mut().fill(val)` (src/main.rs:105) without a download."""
+        """`data_mut().fill(val)` (src/main.rs:105) without a download and without an upload: the device fills."""
         self._host.fill(val)
-        self._stale, self._dirty, self._cells = False, True, []
+        self._stale, self._dirty, self._fill, self._cells = False, False, float(np.float32(val)), []
 
     def copy_from(self, src) -> None:
         """`data_mut().copy_from_slice(src)`: overwrite the whole field (no download first)."""
         np.copyto(self._host, np.asarray(src, np.float32).reshape(self._h, self._w))
-        self._stale, self._dirty, self._cells = False, True, []
+        self._stale, self._dirty, self._fill, self._cells = False, True, None, []
 
     def __getitem__(self, pos):
         x, y = pos
@@ -172,6 +176,9 @@ class FluidSim:
 
     def _inject(self, field, x, y, val):
         check(lib.fruid_fluid_inject(self._h, field, x, y, val))
+
+    def _fill_dev(self, field, val):
+        check(lib.fruid_fluid_fill(self._h, field, val))
 
     def set_iterations(self, k: int) -> None:
         """Sweeps per lin_solve (reference: 20, src/lib.rs:52).  Extension."""
@@ -232,6 +239,9 @@ class DensitySim:
 
     def _inject(self, field, x, y, val):
         check(lib.fruid_density_inject(self._h, field, x, y, val))
+
+    def _fill_dev(self, field, val):
+        check(lib.fruid_density_fill(self._h, field, val))
 
     def set_iterations(self, k: int) -> None:
         check(lib.fruid_density_set_iterations(self._h, k))

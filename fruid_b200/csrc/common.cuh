@@ -104,10 +104,8 @@ __device__ __forceinline__ void pdl_enter_arg(int trigger) {  // same, the switc
 // deterministically instead of once in a few hundred runs.
 #ifdef FRUID_DEBUG
 static __device__ int g_dbg_tail_delay_ns = 0;
-__device__ __forceinline__ void dbg_tail_delay(int warp_in_block) {
-    if (warp_in_block >= 3) return;
-    const int ns = *(volatile int*)&g_dbg_tail_delay_ns;
-    if (ns <= 0) return;
+__device__ __forceinline__ void dbg_tail_delay_ns(int warp_in_block, int ns) {
+    if (warp_in_block >= 3 || ns <= 0) return;
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     do {
@@ -115,9 +113,14 @@ __device__ __forceinline__ void dbg_tail_delay(int warp_in_block) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
     } while (t1 - t0 < (unsigned long long)ns);
 }
+__device__ __forceinline__ void dbg_tail_delay(int warp_in_block) {
+    if (warp_in_block < 3) dbg_tail_delay_ns(warp_in_block, *(volatile int*)&g_dbg_tail_delay_ns);
+}
 #else
 __device__ __forceinline__ void dbg_tail_delay(int) {}
+__device__ __forceinline__ void dbg_tail_delay_ns(int, int) {}
 #endif
+extern int g_dbg_tail_delay_host;  // value of the knob on the host (kernels in other translation units get it as an argument)
 
 // ---- host side of the switch -------------------------------------------------------------------------
 // One copy per process (defined in fruid_abi.cu); the kernels' translation units only see the declarations.

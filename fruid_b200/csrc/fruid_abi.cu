@@ -69,6 +69,7 @@ static bool g_dens_overlap = false;
 // ---- programmatic launch chains (declared in common.cuh) ------------------------------------------------
 namespace fruid {
 PdlState g_pdl;
+int g_dbg_tail_delay_host = 0;
 namespace {
 struct ChainSlot { cudaStream_t st; bool open; };
 thread_local ChainSlot t_chain[16];
@@ -116,11 +117,23 @@ extern "C" int fruid_debug_set_schedule(int mask) {
     g_cfg_epoch.fetch_add(1);
     return 0;
 }
+// Diagnostics: how the library divides by `c` (the cached outcome of the exhaustive reciprocal check): out = {seen, mode}.
+extern "C" int fruid_debug_recip_mode(float c, int* out, float* zhzl) {
+    if (!out || !zhzl) return fail(FRUID_ERR_BAD_ARG, "null out pointer");
+    uint32_t key; memcpy(&key, &c, 4);
+    std::lock_guard<std::mutex> lk(g_recip_mu);
+    auto it = g_recip.find(key);
+    out[0] = it != g_recip.end(); out[1] = out[0] ? it->second.mode : -1;
+    zhzl[0] = out[0] ? it->second.zh : 0.f; zhzl[1] = out[0] ? it->second.zl : 0.f;
+    return 0;
+}
 // FRUID_DEBUG builds: the lowest warps of every block wait `ns` before storing (0 = off).  Release builds: no-op, returns 1.
 extern "C" int fruid_debug_set_tail_delay(int ns) {
 #ifdef FRUID_DEBUG
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpyToSymbol(g_dbg_tail_delay_ns, &ns, sizeof ns));
+    g_dbg_tail_delay_host = ns;
+    g_cfg_epoch.fetch_add(1);  // captured graphs bake the tile kernels' argument in
     return 0;
 #else
     (void)ns;
@@ -274,11 +287,11 @@ extern "C" int fruid_density_download(fruid_density_t* d, int field, float* host
 extern "C" int fruid_density_upload_async(fruid_density_t* d, int field, const float* host) { NEED(d); return d->s.upload_async(field, host); }
 extern "C" int fruid_density_download_async(fruid_density_t* d, int field, float* host) { NEED(d); return d->s.download_async(field, host); }
 extern "C" int fruid_density_inject(fruid_density_t* d, int field, size_t x, size_t y, float val) { NEED(d); return d->s.inject(field, x, y, val); }
-extern "C" int fruid_density_fill(fruid_density_t* d, int field, float val) {
-    NEED(d);
-    FieldSet& s = d->s;
-    if (field < 0 || field > 1) return fail(FRUID_ERR_BAD_ARG, "bad field %d", field);
+// `field.data_mut().fill(val)` (src/main.rs:105-108) on the device.
+static int fill_field(FieldSet& s, int field, float val) {
+    if (field < 0 || field >= s.n_user) return fail(FRUID_ERR_BAD_ARG, "bad field %d", field);
     TRY(s.wait_readers());
+    s.touch();
     if (val == 0.0f && !std::signbit(val)) {
         CU(cudaMemsetAsync(s.buf[field], 0, s.g.pitch * (size_t)s.g.h * sizeof(float), s.stream));
         return 0;
@@ -286,6 +299,8 @@ extern "C" int fruid_density_fill(fruid_density_t* d, int field, float val) {
     LAUNCH("k_fill", s.stream, k_fill<<<cell_grid(s.g.w, s.g.h), cell_block(), 0, s.stream>>>(s.buf[field], s.g, val));
     return 0;
 }
+extern "C" int fruid_density_fill(fruid_density_t* d, int field, float val) { NEED(d); return fill_field(d->s, field, val); }
+extern "C" int fruid_fluid_fill(fruid_fluid_t* f, int field, float val) { NEED(f); return fill_field(f->s, field, val); }
 extern "C" int fruid_density_set_iterations(fruid_density_t* d, int k) { NEED(d); return d->s.set_iters(k); }
 extern "C" int fruid_density_set_fused_sweeps(fruid_density_t* d, int t) { NEED(d); return d->s.set_fused(t); }
 extern "C" int fruid_density_step_dev(fruid_density_t* d, fruid_fluid_t* vel, float dt, float diff) {

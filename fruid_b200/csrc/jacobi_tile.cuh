@@ -277,6 +277,7 @@ static int jacobi_tile_launch(float* out, const float* x, const float* x0, const
     const int num_sms = device_num_sms();
     if (num_sms <= 0) return -4;
     A.pdl_trigger = g_pdl.enabled ? 1 : 0;
+    A.dbg_delay_ns = g_dbg_tail_delay_host;
     const bool pdl = g_pdl.enabled && (pdl_chain_continue(st) || g_pdl.unsafe);
     int r = jacobi_tile_launch_inst_a(R, NW, mode, A, num_sms, pdl, st);
     if (r == -1) r = jacobi_tile_launch_inst_b(R, NW, mode, A, num_sms, pdl, st);

@@ -72,6 +72,7 @@ struct TileArgs {
     float src_dt;
     float* z_out;
     int pdl_trigger;  // programmatic dependent launch: let the successor be scheduled early (host switch)
+    int dbg_delay_ns; // FRUID_DEBUG builds: the lowest warps stall this long before storing (0 = off)
 };
 
 // Work item -> tile.  Tiles touching the domain boundary execute more instructions, so they are
@@ -272,7 +273,7 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
         }
     }
     float4* const xr = v + 1;  // rows 0..R-1 of this warp
-    dbg_tail_delay(wi);
+    dbg_tail_delay_ns(wi, A.dbg_delay_ns);
 
     // ---- store the cells that are H away from every non-domain tile edge -----------------
     (void)FULL;

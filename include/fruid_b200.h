@@ -94,6 +94,9 @@ int fruid_set_launch_overlap(int on);
  * missing dependency into a deterministic mismatch; the release build ignores it and returns 1. */
 int fruid_debug_set_schedule(int mask);
 int fruid_debug_set_tail_delay(int ns);
+/* Diagnostics: out[0] = divisor c seen before, out[1] = the division mode chosen for it (0 IEEE, 4 / 5 verified
+ * reciprocal forms); zhzl = the double-word reciprocal used. */
+int fruid_debug_recip_mode(float c, int *out, float *zhzl);
 
 /* Page-lock / unlock a caller-owned host array (e.g. the Vec<f32> inside an Array2D). */
 int fruid_host_register(void *p, size_t bytes);
@@ -124,6 +127,8 @@ int fruid_fluid_upload_async(fruid_fluid_t *f, int field, const float *host);
 int fruid_fluid_download_async(fruid_fluid_t *f, int field, float *host);
 /* `u[pos] = val` through uv_mut(), src/main.rs:98-102, without a full upload. */
 int fruid_fluid_inject(fruid_fluid_t *f, int field, size_t x, size_t y, float val);
+/* `field.data_mut().fill(val)` without a full upload (cf. fruid_density_fill). */
+int fruid_fluid_fill(fruid_fluid_t *f, int field, float val);
 /* Sweeps per lin_solve; the reference hard-codes 20 (src/lib.rs:52).  Even only. */
 int fruid_fluid_set_iterations(fruid_fluid_t *f, int k);
 /* Jacobi sweeps fused per kernel launch (0 = library default; 1 = one sweep per launch). */

@@ -196,7 +196,7 @@ def test_golden_steps_on_gpu(fb, name):
     sim, den = fb.FluidSim(w, h), fb.DensitySim(w, h)
     _load_fluid(fb, sim, [np.ascontiguousarray(g["in_" + k]) for k in ("u", "v", "u_prev", "v_prev")])
     for k, field in (("dens", 0), ("dens_prev", 1)):
-        fb._lib.check(fb._lib.lib.fruid_density_upload(den._h, field, fb._lib.ptr(np.ascontiguousarray(g["in_" + k]))))
+        fb._lib.check(fb._lib.lib.fruid_density_upload(den._h, field, np.ascontiguousarray(g["in_" + k])))  # the array itself: a temporary's address (ptr()) would dangle
     for _ in range(int(g["nsteps"])):
         sim.step(float(g["dt"]), float(g["visc"]))
         den.step(sim.uv(), float(g["dt"]), float(g["diff"]))

@@ -29,6 +29,7 @@ ap.add_argument("--assert-safe", action="store_true")
 ap.add_argument("--json", default="")
 ap.add_argument("--repeat", type=int, default=1)
 ap.add_argument("--quick", action="store_true", help="fewer schedules (the pytest wrapper)")
+ap.add_argument("--only", default="", help="run only the cases whose name contains this")
 args = ap.parse_args()
 
 import fruid_b200 as fb  # noqa: E402
@@ -41,20 +42,40 @@ debug_build = "FRUID_DEBUG" in info
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-def bits_bad(a, b):
+DETAILS = []
+
+
+def bits_bad(a, b, name=""):
     a = np.ascontiguousarray(a, np.float32)
     b = np.ascontiguousarray(b, np.float32)
-    return int(np.count_nonzero(~((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b)))))
+    bad = ~((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b)))
+    n = int(np.count_nonzero(bad))
+    if n and len(DETAILS) < 12:
+        ys, xs = np.nonzero(bad)
+        with np.errstate(all="ignore"):
+            rel = float(np.nanmax(np.abs(a - b)[bad] / np.maximum(np.abs(b[bad]), 1e-30))) if n else 0.0
+        DETAILS.append({"field": name, "cells": n, "nan_got": int(np.isnan(a).sum()), "rows": sorted(set(ys.tolist()))[:12],
+                        "max_rel": rel, "first": [(int(x), int(y), float(a[y, x]), float(b[y, x])) for y, x in list(zip(ys, xs))[:4]]})
+    return n
 
 
 def case_golden(name):
     g = np.load(os.path.join(GOLD, name))
     w, h = int(g["w"]), int(g["h"])
     sim, den = fb.FluidSim(w, h), fb.DensitySim(w, h)
-    for k, f in (("u", 0), ("v", 1), ("u_prev", 2), ("v_prev", 3)):
-        _lib.check(L.fruid_fluid_upload(sim._h, f, _lib.ptr(np.ascontiguousarray(g["in_" + k]))))
-    for k, f in (("dens", 0), ("dens_prev", 1)):
-        _lib.check(L.fruid_density_upload(den._h, f, _lib.ptr(np.ascontiguousarray(g["in_" + k]))))
+    # the arrays must stay referenced across the C call: `ptr(np.ascontiguousarray(..))` on a temporary hands the
+    # library the address of memory that Python has already freed (the round-1 "intermittent mismatch")
+    keep = {k: np.ascontiguousarray(g["in_" + k]) for k in ("u", "v", "u_prev", "v_prev", "dens", "dens_prev")}
+    if os.environ.get("FRUID_PROBE_TEMPORARIES") == "1":  # reproduce the round-1 test bug on purpose
+        for k, f in (("u", 0), ("v", 1), ("u_prev", 2), ("v_prev", 3)):
+            _lib.check(L.fruid_fluid_upload(sim._h, f, _lib.ptr(np.ascontiguousarray(g["in_" + k]))))
+        for k, f in (("dens", 0), ("dens_prev", 1)):
+            _lib.check(L.fruid_density_upload(den._h, f, _lib.ptr(np.ascontiguousarray(g["in_" + k]))))
+    else:
+        for k, f in (("u", 0), ("v", 1), ("u_prev", 2), ("v_prev", 3)):
+            _lib.check(L.fruid_fluid_upload(sim._h, f, _lib.ptr(keep[k])))
+        for k, f in (("dens", 0), ("dens_prev", 1)):
+            _lib.check(L.fruid_density_upload(den._h, f, _lib.ptr(keep[k])))
     for _ in range(int(g["nsteps"]) ):
         sim.step(float(g["dt"]), float(g["visc"]))
         den.step(sim.uv(), float(g["dt"]), float(g["diff"]))
@@ -62,13 +83,13 @@ def case_golden(name):
     for k, f in (("u", 0), ("v", 1), ("u_prev", 2), ("v_prev", 3)):
         a = np.empty((h, w), np.float32)
         _lib.check(L.fruid_fluid_download(sim._h, f, _lib.ptr(a)))
-        n = bits_bad(a, g["out_" + k])
+        n = bits_bad(a, g["out_" + k], k)
         if n:
             bad[k] = n
     for k, f in (("dens", 0), ("dens_prev", 1)):
         a = np.empty((h, w), np.float32)
         _lib.check(L.fruid_density_download(den._h, f, _lib.ptr(a)))
-        n = bits_bad(a, g["out_" + k])
+        n = bits_bad(a, g["out_" + k], k)
         if n:
             bad[k] = n
     return bad
@@ -110,7 +131,12 @@ def case_random(w, h, steps, visc, diff, ndyes, seed, change_dt=False):
     for d in dyes:
         got += [d.density().numpy(), d.density_mut().numpy()]
     names = ["u", "v", "u_prev", "v_prev"] + [f"{n}{i}" for i in range(ndyes) for n in ("dens", "dens_prev")]
-    return {n: bits_bad(g, wnt) for n, g, wnt in zip(names, got, want) if bits_bad(g, wnt)}
+    out = {}
+    for n, g, wnt in zip(names, got, want):
+        k = bits_bad(g, wnt, n)
+        if k:
+            out[n] = k
+    return out
 
 
 CASES = [
@@ -136,13 +162,24 @@ for graphs, pdl, overlap, fork, unchained in combos:
     if debug_build:
         _lib.check(L.fruid_debug_set_tail_delay(args.delay_ns))
     for name, fn in CASES:
+        if args.only and args.only not in name:
+            continue
         for rep in range(args.repeat):
             bad = fn()
+            print("run", graphs, pdl, overlap, fork, unchained, name, "bad" if bad else "ok", flush=True)
             rec = {"graphs": graphs, "pdl": pdl, "dens_overlap": overlap, "vel_fork": fork, "unchained": unchained,
                    "case": name, "rep": rep, "mismatching_cells": bad}
             results.append(rec)
             if bad:
                 print("MISMATCH", json.dumps(rec), flush=True)
+                while DETAILS:
+                    print("   ", json.dumps(DETAILS.pop(0)), flush=True)
+                if name.startswith("golden37"):
+                    import ctypes
+                    for cc in (np.float32(1.0) + np.float32(4.0) * np.float32(np.float32(np.float32(np.float32(0.05) * np.float32(v)) * np.float32(35)) * np.float32(27)) for v in (2e-4, 1e-4)):
+                        o, z = (ctypes.c_int * 2)(), (ctypes.c_float * 2)()
+                        L.fruid_debug_recip_mode(float(cc), ctypes.cast(o, ctypes.c_void_p), ctypes.cast(z, ctypes.c_void_p))
+                        print("    recip", float(cc), list(o), [float(z[0]).hex(), float(z[1]).hex()], flush=True)
                 if not unchained:
                     fails_safe += 1
 L.fruid_debug_set_schedule(2)
