@@ -52,7 +52,7 @@ class _vp(ctypes.c_void_p):
 
     @classmethod
     def from_param(cls, obj):
-        if isinstance(obj, np.ndarray):
+        if np is not None and isinstance(obj, np.ndarray):  # (np is None while the interpreter shuts down)
             if obj.dtype != np.float32 or not obj.flags.c_contiguous:
                 raise TypeError("expected a C-contiguous float32 array")
             return ctypes.c_void_p(obj.ctypes.data)

@@ -61,10 +61,12 @@ extern "C" const char* fruid_build_info(void) {
 }
 
 static bool g_vel_fork = true;      // u and v diffuse on two streams
-// Density add_source + diffuse beside the velocity step still in flight (only the advect waits for u, v).
-// FRUID_B200_DENS_OVERLAP=1 / fruid_debug_set_schedule turn it on; default: one captured graph of the whole density step
-// after the velocity step.
-static bool g_dens_overlap = false;
+// Density add_source + diffuse beside the velocity step still in flight (only the advect waits for u, v): on by
+// default (250^2 scene step 85 -> 70 us, 4096^2 1.15 -> 1.135 ms).  FRUID_B200_DENS_OVERLAP=0 / fruid_debug_set_schedule
+// select one captured graph of the whole density step after the velocity step instead.  (Round 1 kept this off
+// because of an "intermittent mismatch" that turned out to be a use-after-free in the TEST; every
+// schedule is now checked on the FRUID_DEBUG build with delayed stores, tests/test_ordering_gpu.py.)
+static bool g_dens_overlap = true;
 
 // ---- programmatic launch chains (declared in common.cuh) ------------------------------------------------
 namespace fruid {

@@ -177,34 +177,71 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
         : "memory");
 }
 
-// EDGE tiles: flags saying which of my components sit next to a domain border column
-// (gx == 1: left neighbour is border column 0; gx == w-2: right neighbour is column w-1).
-struct EdgeFlags { bool l1, r0, r1, r2, r3, negx, negy; int h; float zh, zl; };
+// Boundary handling inside the sweeps ("set_bnd in registers", lib.rs:27-44 after every sweep, lib.rs:69).
+// A tile that contains a domain border keeps the border cells of its register copy equal to what set_bnd would
+// have written: after every sweep the thread (column borders) or warp (row borders) that holds a border cell
+// overwrites it with sigma * (adjacent interior cell of the new iterate).  Sweep 1 therefore reads the incoming
+// border as loaded (lib.rs:56-59 read x before any set_bnd) and later sweeps read what set_bnd left there; the
+// stencil itself is the interior code, unchanged.  Corners are never read by the 5-point stencil; the store phase
+// produces them (and the border rows / columns of the final iterate) exactly.
+//   EDGE = 0  interior tile: nothing to do
+//   EDGE = 1  the tile holds the top and/or bottom domain row (and no left/right domain column): a few
+//             warp-uniform fixups per SWEEP
+//   EDGE = 2  the tile also holds the left and/or right domain column: per-lane selects per row as well
+struct EdgeFlags {
+    bool negx, negy;
+    bool pl;            // my .x is border column 0
+    bool p1, p2, p3;    // my .y / .z / .w is border column w-1 (its source, column w-2, is my previous component)
+    bool p0r;           // my .w is column w-2 and border column w-1 is the next lane's .x: mirror on read
+    bool top;           // this warp holds global rows 0 (border) and 1 in its first two rows
+    unsigned bot;       // bit r set: my row r is global row gh-2, whose lower neighbour is border row gh-1
+    float zh, zl;
+};
+// sigma * v selected without touching the FP32 pipe (sign flip = integer XOR; the select is an ALU-pipe FSEL).
+__device__ __forceinline__ float sel_mirror(bool take, unsigned flip, float src, float keep) {
+    return take ? __uint_as_float(__float_as_uint(src) ^ flip) : keep;
+}
+__device__ __forceinline__ float4 sel_mirror4(bool take, unsigned flip, float4 src, float4 keep) {
+    return make_float4(sel_mirror(take, flip, src.x, keep.x), sel_mirror(take, flip, src.y, keep.y),
+                       sel_mirror(take, flip, src.z, keep.z), sel_mirror(take, flip, src.w, keep.w));
+}
 
-// New value of one float4 row from its old value cc, the rows above/below and x0 (z).
-template <int MODE, bool EDGE>
+// New value of one float4 row from its old value cc, the rows above/below and x0 (z).  Boundary rows and columns
+// are handled by selects on the operands / results (no branches: a divergent branch per row costs more than the
+// whole stencil):
+//   rows     TOPROW (a constant after unrolling: this is warp-row 1): if the warp holds the top border, `up` = sy * cc (lib.rs:36);
+//            any row: if it is global row gh-2 (E.bot), `dn` = sy * cc (lib.rs:37)
+//   columns  the border cells of the NEW row are set to sx * their neighbour (lib.rs:31-32), so the next sweep reads
+//            them like any other cell; a border column in the next lane's .x is mirrored on read instead (p0r)
+// `sub` is false in the first sweep of a launch, which reads the incoming border as loaded (lib.rs:56-59).
+template <int MODE, int EDGE>
 __device__ __forceinline__ float4 jac_row_full(float4 cc, float4 up, float4 dn, const float4 z, float a, float c,
-                                               const EdgeFlags& E, bool sub, int gy) {
+                                               const EdgeFlags& E, bool sub, bool isbot, const bool TOPROW) {
     const unsigned FULL = 0xffffffffu;
     float lft = __shfl_up_sync(FULL, cc.w, 1);
     float rgt = __shfl_down_sync(FULL, cc.x, 1);
-    float ly = cc.x, rx = cc.y, ry = cc.z, rz = cc.w;
-    if (EDGE) {
-        if (sub && gy == 1) up = sgn4(E.negy, cc);           // row 0 = sy * row 1       (lib.rs:36)
-        if (sub && gy == E.h - 2) dn = sgn4(E.negy, cc);     // row ny+1 = sy * row ny   (lib.rs:37)
-        if (sub && E.l1) ly = sgn(E.negx, cc.y);             // col 0 = sx * col 1       (lib.rs:31)
-        if (sub && E.r0) rx = sgn(E.negx, cc.x);             // col nx+1 = sx * col nx   (lib.rs:32)
-        if (sub && E.r1) ry = sgn(E.negx, cc.y);
-        if (sub && E.r2) rz = sgn(E.negx, cc.z);
-        if (sub && E.r3) rgt = sgn(E.negx, cc.w);
+    if (EDGE >= 1) {
+        const unsigned fy = E.negy ? 0x80000000u : 0u;
+        if (TOPROW) up = sel_mirror4(sub && E.top, fy, cc, up);
+        dn = sel_mirror4(sub && isbot, fy, cc, dn);
     }
-    const float t0 = fadd(lft, rx), t1 = fadd(ly, ry), t2 = fadd(cc.y, rz), t3 = fadd(cc.z, rgt);  // l + r
-    return jac_row<MODE>(z, t0, t1, t2, t3, up, dn, a, c, E.zh, E.zl);
+    const unsigned fx = E.negx ? 0x80000000u : 0u;
+    if (EDGE == 2) rgt = sel_mirror(sub && E.p0r, fx, cc.w, rgt);
+    const float t0 = fadd(lft, cc.y), t1 = fadd(cc.x, cc.z), t2 = fadd(cc.y, cc.w), t3 = fadd(cc.z, rgt);  // l + r
+    float4 nv = jac_row<MODE>(z, t0, t1, t2, t3, up, dn, a, c, E.zh, E.zl);
+    if (EDGE == 2) {  // column borders of the new iterate
+        nv.x = sel_mirror(E.pl, fx, nv.y, nv.x);
+        nv.y = sel_mirror(E.p1, fx, nv.x, nv.y);
+        nv.z = sel_mirror(E.p2, fx, nv.y, nv.z);
+        nv.w = sel_mirror(E.p3, fx, nv.z, nv.w);
+    }
+    return nv;
 }
 
-template <int R, int NW, int MODE, bool EDGE>
+template <int R, int NW, int MODE, int EDGE>
 __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int ky, float4 (&v)[R + 1],
                                                  float4 (&z)[R], float4* __restrict__ halo) {
+    static_assert(R >= 2, "a warp must hold a border row together with its neighbour");
     constexpr int TH = R * NW;
     constexpr int HB = (NW * 2 + 2) * 32;  // float4 slots per halo buffer (one guard row at each end)
     const unsigned FULL = 0xffffffffu;
@@ -218,12 +255,19 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
     const float a = A.a, c = A.c;
 
     EdgeFlags E;
-    E.l1 = E.r0 = E.r1 = E.r2 = E.r3 = false;
-    E.negx = negx; E.negy = negy; E.h = g.gh;
+    E.negx = negx; E.negy = negy;
+    E.pl = E.p1 = E.p2 = E.p3 = E.p0r = E.top = false;
+    E.bot = 0u;
     E.zh = A.zh; E.zl = A.zl;
-    if (EDGE) {
-        E.l1 = (gx0 + 1 == 1);  // ox == 0 && lane == 0 (tile origins are multiples of 4)
-        E.r0 = (gx0 + 0 == g.w - 2); E.r1 = (gx0 + 1 == g.w - 2); E.r2 = (gx0 + 2 == g.w - 2); E.r3 = (gx0 + 3 == g.w - 2);
+    if (EDGE >= 1) {
+        E.top = (gyg == 0);
+        const int rb = g.gh - 2 - gyg;  // my row that is global row gh-2, if any
+        if (rb >= 0 && rb < R) E.bot = 1u << rb;
+    }
+    if (EDGE == 2) {
+        E.pl = (gx0 == 0);
+        E.p1 = (gx0 + 1 == g.w - 1); E.p2 = (gx0 + 2 == g.w - 1); E.p3 = (gx0 + 3 == g.w - 1);
+        E.p0r = (gx0 + 4 == g.w - 1);
     }
 
     if (A.fuse_src) {  // add_source: x0[k] = x0[k] + s[k]*dt on every cell (border included)
@@ -251,9 +295,9 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
             const float4 hbot = hw[HB + 64];
             const bool sub = EDGE && (s > 1);
 #pragma unroll
-            for (int r = 1; r <= R; ++r)
-                v[r - 1] = jac_row_full<MODE, EDGE>(v[r], v[r - 1], (r == R) ? hbot : v[r + 1], z[r - 1], a, c, E,
-                                                    sub, gyg + r - 1);
+            for (int r = 1; r <= R; ++r)  // warp-row r-1
+                v[r - 1] = jac_row_full<MODE, EDGE>(v[r], v[r - 1], (r == R) ? hbot : v[r + 1], z[r - 1], a, c, E, sub,
+                                                    EDGE && ((E.bot >> (r - 1)) & 1u), r == 2);
         }
         if (s + 1 > A.T) {  // odd T: move the rows back to v[1..R] for the store phase
 #pragma unroll
@@ -267,9 +311,9 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
             v[R] = hw[64];
             const float4 htop = hw[-32];
 #pragma unroll
-            for (int r = R - 1; r >= 0; --r)
-                v[r + 1] = jac_row_full<MODE, EDGE>(v[r], (r == 0) ? htop : v[r - 1], v[r + 1], z[r], a, c, E, EDGE,
-                                                    gyg + r);
+            for (int r = R - 1; r >= 0; --r)  // warp-row r
+                v[r + 1] = jac_row_full<MODE, EDGE>(v[r], (r == 0) ? htop : v[r - 1], v[r + 1], z[r], a, c, E, EDGE != 0,
+                                                    EDGE && ((E.bot >> r) & 1u), r == 1);
         }
     }
     float4* const xr = v + 1;  // rows 0..R-1 of this warp
@@ -384,6 +428,38 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
     }
 }
 
+// One tile: staging -> registers, prefetch of the next tile, T sweeps, stores.
+template <int R, int NW, int MODE, int EDGE>
+__device__ __forceinline__ void jacobi_tile_run(const TileArgs& A, int kx, int ky, float* zs, float* xs, float4* halo,
+                                                uint64_t* mbar, volatile int* s_next, int next, int ntiles, uint32_t tx_bytes) {
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    // Staging -> registers: the iterate and the right-hand side stay there for all T sweeps.
+    float4 v[R + 1], z[R];
+    {
+        const float4* xrow = reinterpret_cast<const float4*>(xs) + (wi * R) * 32 + lane;
+        const float4* zrow = reinterpret_cast<const float4*>(zs) + (wi * R) * 32 + lane;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            v[r + 1] = A.x_is_zero ? make_float4(0.f, 0.f, 0.f, 0.f) : xrow[r * 32];
+            z[r] = zrow[r * 32];
+        }
+        v[0] = v[1];
+    }
+    __syncthreads();  // staging buffers are free again (and the previous tile's halo reads are done)
+    if (threadIdx.x == 0) {  // prefetch the next tile behind this tile's sweeps
+        *s_next = next;      // read by everyone after the sweeps' barriers
+        if (next < ntiles) {
+            int nkx, nky;
+            tile_of_item(next, A.ntx, A.nty, nkx, nky);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before async writes
+            mbar_expect_tx(mbar, tx_bytes);
+            tma_load_2d(zs, &A.tm_x0, nkx * A.SX, nky * A.SY, mbar);
+            if (!A.x_is_zero) tma_load_2d(xs, &A.tm_x, nkx * A.SX, nky * A.SY, mbar);
+        }
+    }
+    jacobi_tile_body<R, NW, MODE, EDGE>(A, kx, ky, v, z, halo);
+}
+
 template <int R, int NW>
 constexpr size_t jacobi_tile_smem_bytes() {
     // TMA staging of the next tile's x0 and x + halo exchange (2 buffers, NW*2+2 rows of 512 B) + mbarrier
@@ -430,38 +506,18 @@ __global__ void __launch_bounds__(NW * 32, 1) k_jacobi_tile(const __grid_constan
         mbar_wait(mbar, phase);  // this tile's x0 (and x) have landed in the staging buffers
         phase ^= 1u;
 
-        // Staging -> registers: the iterate and the right-hand side stay there for all T sweeps.
-        float4 v[R + 1], z[R];
-        {
-            const float4* xrow = reinterpret_cast<const float4*>(xs) + (wi * R) * 32 + lane;
-            const float4* zrow = reinterpret_cast<const float4*>(zs) + (wi * R) * 32 + lane;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                v[r + 1] = A.x_is_zero ? make_float4(0.f, 0.f, 0.f, 0.f) : xrow[r * 32];
-                z[r] = zrow[r * 32];
-            }
-            v[0] = v[1];
-        }
-        __syncthreads();  // staging buffers are free again (and the previous tile's halo reads are done)
-        slot ^= 1;
-        if (threadIdx.x == 0) {  // prefetch the next tile behind this tile's sweeps
-            s_item[slot] = next;  // read by everyone after the sweeps' barriers
-            if (next < ntiles) {
-                int nkx, nky;
-                tile_of_item(next, A.ntx, A.nty, nkx, nky);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before async writes
-                mbar_expect_tx(mbar, tx_bytes);
-                tma_load_2d(zs, &A.tm_x0, nkx * A.SX, nky * A.SY, mbar);
-                if (!A.x_is_zero) tma_load_2d(xs, &A.tm_x, nkx * A.SX, nky * A.SY, mbar);
-            }
-        }
+        // The three boundary classes (see jacobi_tile_body) are three self-contained code paths, each loading its own
+        // registers from the staging buffers: sharing the register copy across them costs register moves in all three.
         const int ox = kx * A.SX, oy = ky * A.SY;
-        const bool edge = (kx == 0) || (ox + 128 >= A.g.w - 1) || (oy + A.g.gy0 <= 1) || (oy + TH + A.g.gy0 >= A.g.gh - 1) ||
-                          (ky == 0) || (ky == A.nty - 1);  // slab cuts take the general store path too
-        if (edge)
-            jacobi_tile_body<R, NW, MODE, true>(A, kx, ky, v, z, halo);
+        const bool xedge = (kx == 0) || (ox + 128 >= A.g.w - 1);
+        const bool yedge = (oy + A.g.gy0 <= 1) || (oy + TH + A.g.gy0 >= A.g.gh - 1) || (ky == 0) || (ky == A.nty - 1);
+        slot ^= 1;
+        if (xedge)
+            jacobi_tile_run<R, NW, MODE, 2>(A, kx, ky, zs, xs, halo, mbar, s_item + slot, next, ntiles, tx_bytes);
+        else if (yedge)
+            jacobi_tile_run<R, NW, MODE, 1>(A, kx, ky, zs, xs, halo, mbar, s_item + slot, next, ntiles, tx_bytes);
         else
-            jacobi_tile_body<R, NW, MODE, false>(A, kx, ky, v, z, halo);
+            jacobi_tile_run<R, NW, MODE, 0>(A, kx, ky, zs, xs, halo, mbar, s_item + slot, next, ntiles, tx_bytes);
     }
     // The last CTA to leave resets the scheduler for the next launch on this stream.
     if (threadIdx.x == 0) {

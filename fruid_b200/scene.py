@@ -47,7 +47,10 @@ class Scene:
         time = F(self.frame_count) / F(12.0)
         cx, cy = w // 2, h // 2
         x = F(cx) * (np.cos(time / F(5.0), dtype=F) + F(1.0))
-        px = int(x)  # `x as usize`; x >= 0 here
+        # `x as usize`; x >= 0 here.  When cos() rounds to exactly 1.0 (first at frame 377: 377/60 is within 1.5e-4
+        # of 2*pi) x equals the width and the reference's `u[pos] = ..` panics (index out of bounds, main.rs:100-101);
+        # the headless driver keeps running with the cell clamped to the last column ("guard px < w").
+        px = min(int(x), w - 1)
         u_val = F(-4500.0) * np.cos(time * F(3.0), dtype=F)
         v_val = F(-4500.0) * np.sin(time * F(3.0), dtype=F)
         return (px, cy), u_val, v_val
@@ -56,7 +59,7 @@ class Scene:
         self.frame_count += 1                                     # main.rs:91
         pos, u_val, v_val = self.injection()
         u, v = self.sim.uv_mut()                                  # main.rs:98
-        u[pos] = u_val                                            # main.rs:101 (panics if px == w)
+        u[pos] = u_val                                            # main.rs:101
         v[pos] = v_val                                            # main.rs:102
         for d in self.dyes:                                       # main.rs:105-108
             d.density_mut().fill(0.0)

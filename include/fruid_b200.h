@@ -70,7 +70,7 @@ const char *fruid_build_info(void);
 
 /* Tuning knob: tile shape of the fused Jacobi kernel (rows per warp x warps per CTA; the tile
  * is 128 x rows_per_warp*warps cells) and the default number of fused sweeps (0 = keep).
- * By default the library chooses per launch: 128x128 tiles and 10 sweeps per launch, smaller tiles
+ * By default the library chooses per launch: 128x140 tiles (7 rows x 20 warps) and 10 sweeps per launch, smaller tiles
  * (128x64, 128x96) and up to 20 sweeps on grids too small to give every SM a tile.  A call pins the
  * shape for every later launch; (0, 0, T) returns to the automatic choice.  Results never change. */
 int fruid_set_tile_config(int rows_per_warp, int warps, int default_fused);

@@ -76,6 +76,18 @@ def main():
             "probe": {k: float(a[2 * h // 3, 2 * w // 3]) for k, a in fl.items()},  # cf. dbg! at main.rs:54
             "absmax": {k: float(np.abs(a).max()) for k, a in fl.items()},
         }
+    # BASELINE.json configs[1]: 1024 x 1024, one dye, the reference's injection law, 1000 frames (and a 200-frame run with
+    # visc = diff = 1e-6, SURVEY 8d "variant B"); the oracle's OpenMP / cache-friendly traversal, bit-identical to the
+    # faithful one (tests/test_oracle.py)
+    for (w, h, frames, visc, diff) in ((1024, 1024, 1000, 0.0, 0.0), (1024, 1024, 200, 1e-6, 1e-6)):
+        s = Scene(OFluidSim, ODensitySim, w, h, n_dyes=1)
+        s.run(frames, visc=visc, diff=diff)
+        fl = scene_fields(s)
+        sums[f"{w}x{h}_f{frames}_d1" + ("" if visc == 0.0 else "_visc")] = {
+            "sha256": {k: sha(a) for k, a in fl.items()},
+            "probe": {k: float(a[2 * h // 3, 2 * w // 3]) for k, a in fl.items()},
+            "absmax": {k: float(np.abs(a).max()) for k, a in fl.items()},
+        }
     with open(os.path.join(HERE, "scene_checksums.json"), "w") as fh:
         json.dump(sums, fh, indent=1, sort_keys=True)
     print("golden fixtures written to", HERE)

@@ -439,6 +439,19 @@ def test_config1_scale_short(fb, oracle_mod, w, h):
         assert_bits(fa[k], fo[k], k)
 
 
+@pytest.mark.parametrize("key,frames,visc", [("1024x1024_f1000_d1", 1000, 0.0), ("1024x1024_f200_d1_visc", 200, 1e-6)])
+def test_config1_full_length_checksums(fb, key, frames, visc):
+    """BASELINE.json configs[1] at full length: 1024 x 1024, one dye, the injection law of src/main.rs:91-102,
+    1000 frames (and 200 frames with visc = diff = 1e-6), SHA-256 of every field against the oracle run recorded by
+    tests/golden/make_golden.py."""
+    from fruid_b200.scene import Scene
+    sums = json.load(open(os.path.join(GOLD, "scene_checksums.json")))[key]
+    s = Scene(fb.FluidSim, fb.DensitySim, 1024, 1024, n_dyes=1)
+    s.run(frames, visc=visc, diff=visc)
+    for k, a in _scene_fields(s).items():
+        assert hashlib.sha256(a.tobytes()).hexdigest() == sums["sha256"][k], k
+
+
 def test_cpp_mirror_runs_a_step(fb, tmp_path):
     """include/fruid.hpp (the C++ mirror of the crate API) against the same library."""
     import subprocess
@@ -651,6 +664,22 @@ def test_iteration_sweep_config3(fb, oracle_mod, iters):
     a = np.empty((h, w), np.float32)
     fb._lib.check(L.fruid_density_download(den._h, 0, fb._lib.ptr(a)))
     assert_bits(a, od.dens, "dens")
+
+
+@pytest.mark.parametrize("iters", [40, 100, 200, 500])
+def test_iteration_sweep_config3_full_size(fb, oracle_mod, iters):
+    """BASELINE.json configs[3] at its full size: one scene step at 4096 x 4096 with K = 40 ... 500 sweeps per lin_solve
+    against the oracle (OpenMP traversal, bit-identical to the faithful one), every field, bit for bit."""
+    n = 4096
+    sc = _scene_fields_big(n)
+    got = _run_handles(fb, n, sc, 1, 0.0, iters=iters)
+    of, od = oracle_mod.Fluid(n, n, iters=iters), oracle_mod.Density(n, n, iters=iters)
+    of.u[:], of.v[:], of.u_prev[:], of.v_prev[:] = sc["u"], sc["v"], sc["u_prev"], sc["v_prev"]
+    od.dens[:], od.dens_prev[:] = sc["dens"], sc["dens_prev"]
+    of.step(0.01, 0.0)
+    od.step((of.u, of.v), 0.01, 0.0)
+    for g, want, name in zip(got, (of.u, of.v, of.u_prev, of.v_prev, od.dens, od.dens_prev), NAMES6):
+        assert_bits(g, want, f"{name} (K={iters})")
 
 
 def test_x_mirror_symmetry_of_the_pressure_solve_at_full_size(fb):

@@ -75,12 +75,12 @@ def test_automatic_shape_policy(L):
     assert plan(L, 512, 512)[1][:3] == [3, 16, 10]
     assert plan(L, 1024, 1024)[1][:3] == [4, 24, 10]
     for n in (1536, 2048, 4096, 16384):
-        assert plan(L, n, n)[1][:3] == [8, 16, 10]
+        assert plan(L, n, n)[1][:3] == [7, 20, 10]
     # an explicit fused depth is respected (and moves to a shape that supports it)
     rc, p = plan(L, 250, 250, 20, 20)
     assert rc == 0 and p[2] == 20 and (p[0] * p[1]) // 2 - 2 >= 20
     rc, p = plan(L, 4096, 4096, 20, 4)
-    assert rc == 0 and p[:3] == [8, 16, 4] and p[5] == 5
+    assert rc == 0 and p[:3] == [7, 20, 4] and p[5] == 5
     assert plan(L, 4096, 4096, 20, 1)[1][2] == 1               # one plain kernel per sweep
 
 
