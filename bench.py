@@ -406,8 +406,13 @@ def load_peaks():
         return {}
 
 
-def roofline_of(stats, wl, scene_steps, value, clocks):
-    """The dominant kernel (the fused Jacobi kernel) from a per-kernel CUDA-event pass."""
+def roofline_of(stats, wl, scene_steps, value, clocks, in_step_us_per_sweep=None):
+    """The dominant kernel (the fused Jacobi kernel).  Its launch duration comes from CUDA events over timed regions of
+    the real step loop (graph replay, programmatic launch, the density stream running beside the velocity stream): the
+    same loop is timed at K and at 2K sweeps per lin_solve and the difference is divided by the extra launches
+    (`in_step_us_per_sweep`).  The per-kernel pass that brackets every launch with its own events (profiling mode: direct
+    launches, nothing overlapped) gives the kernel's share of the step and the other kernels' times; its launch time is
+    kept as `avg_launch_us_isolated`."""
     peaks = load_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     w, h = wl.w, wl.h
@@ -417,7 +422,8 @@ def roofline_of(stats, wl, scene_steps, value, clocks):
     dom_launches, dom_ms = stats[dom_name]
     sweeps_per_launch = (4 + wl.dyes) * wl.iters * scene_steps / dom_launches
     alg_bytes = 12.0 * w * h * sweeps_per_launch      # 12 B/cell/sweep
-    avg_s = dom_ms * 1e-3 / dom_launches
+    iso_s = dom_ms * 1e-3 / dom_launches
+    avg_s = in_step_us_per_sweep * 1e-6 * sweeps_per_launch if in_step_us_per_sweep else iso_s
     achieved = alg_bytes / avg_s / 1e9
     traffic = None
     try:
@@ -442,7 +448,9 @@ def roofline_of(stats, wl, scene_steps, value, clocks):
             "dram_frac_actual": (traffic / avg_s / 1e9 / peak) if traffic else None,
             "fp32_pipe_frac": fp32,
             "fp32_pipe_note": f"5 FP32 lane-ops per cell-sweep / (148 SMs x 128 lanes x {mhz:.0f} MHz), halo recompute excluded",
-            "sweeps_per_launch": sweeps_per_launch, "avg_launch_us": avg_s * 1e6,
+            "sweeps_per_launch": sweeps_per_launch, "avg_launch_us": avg_s * 1e6, "avg_launch_us_isolated": iso_s * 1e6,
+            "launch_time_method": ("CUDA events over the timed step loop at K and 2K sweeps per lin_solve: (t(2K) - t(K)) / extra "
+                                   "launches" if in_step_us_per_sweep else "CUDA events around every launch (profiling pass)"),
             "algorithmic_bytes_per_launch": alg_bytes, "kernel_share_of_step": dom_ms / tot_ms,
             "kernels_ms_per_step": {k: round(t / scene_steps, 4) for k, (n, t) in sorted(stats.items())},
             "kernels_launches_per_step": {k: n / scene_steps for k, (n, t) in sorted(stats.items())},
@@ -500,14 +508,25 @@ def run_b200(args):
         sustained = {"value": wl.w * wl.h * n_s / (ms_s * 1e-3), "unit": "cell-steps/s", "steps": n_s, "seconds": ms_s * 1e-3,
                      "ms_per_step": ms_s / n_s, "clocks": clk_s.summary()}
 
-    # ---- per-kernel timing pass (roofline of the dominant kernel) ----
+    # ---- the fused Jacobi kernel's time per sweep inside the real step loop: the same loop at 2K sweeps ----
+    in_step = None
+    if not wl.frame_inputs:
+        n2 = max(3, min(steps, 10))
+        ms_k = timed(torch, rig, stream, n2, 1) / n2
+        rig.set_iterations(2 * wl.iters)
+        ms_2k = timed(torch, rig, stream, n2, 2) / n2
+        rig.set_iterations(wl.iters)
+        timed(torch, rig, stream, 1, 1)
+        in_step = (ms_2k - ms_k) * 1e3 / ((4 + wl.dyes) * wl.iters)   # us per sweep of one field
+
+    # ---- per-kernel timing pass (shares of the step, the other kernels) ----
     nprof = max(2, min(steps, 5))
     _lib.profile_enable(True)
     for _ in range(nprof):
         rig.step()
     stats = _lib.profile_report()
     _lib.profile_enable(False)
-    roofline = roofline_of(stats, wl, nprof, value, clocks)
+    roofline = roofline_of(stats, wl, nprof, value, clocks, in_step)
 
     # ---- variants on the headline workload ----
     variants = {}
@@ -688,15 +707,33 @@ def run_e2e(args, fb, torch, wl):
 
 
 def run_e2e_frames(args, fb, torch, wl):
-    """The reference's frame through the crate-API mirror (fruid_b200.api, the Python twin of rust/src/lib.rs and
-    include/fruid.hpp), literally main.rs:94-118: one-cell writes through uv_mut(), density_mut().fill(0) on every dye,
-    sim.step, the dyes' step(sim.uv(), ..), then -- what the viewer's draw_density (main.rs:124,146-183) needs -- the
-    RGB of every cell computed on the device and copied to the host.  Host <-> device bytes are what the mirror
-    actually moves per frame (counted from the calls it makes)."""
+    """The reference's frame through the compiled crate-API mirror (include/fruid.hpp, the C++ twin of rust/src/lib.rs),
+    literally main.rs:94-124: one-cell writes through uv_mut(), density_mut().data_mut().fill(0) on the four dyes,
+    sim.step, the dyes' step(sim.uv(), ..), then -- what draw_density (main.rs:146-183) needs -- the RGB of every cell
+    computed on the device and copied to the host.  Run by fruid_b200/lib/frame_e2e (fruid_b200/host/frame_e2e.cpp);
+    the host <-> device bytes are what the mirror actually moved per frame (counted where it calls the C ABI).  The same
+    frame through the Python mirror (fruid_b200.api) is reported beside it."""
+    import subprocess
     from fruid_b200 import _lib
+    from fruid_b200.build import FRAME_E2E
     from fruid_b200.scene import Scene
     L = _lib.lib
     w, h = wl.w, wl.h
+    n = args.steps if args.steps is not None else (wl.steps or 100)
+    n = max(2, min(n, 1000))
+    out = {"unit": "cell-steps/s", "steps": n}
+    if wl.dyes == 4:
+        r = subprocess.run([FRAME_E2E, str(w), str(h), str(n), "5", "1"], capture_output=True, text=True, timeout=600)
+        cpp = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stdout + r.stderr}
+        r2 = subprocess.run([FRAME_E2E, str(w), str(h), str(n), "5", "0"], capture_output=True, text=True, timeout=600)
+        cpp_unbatched = json.loads(r2.stdout.strip().splitlines()[-1]) if r2.returncode == 0 else {"error": r2.stdout + r2.stderr}
+        if "us_per_frame" in cpp:
+            out.update({"value": w * h / (cpp["us_per_frame"] * 1e-6), "us_per_frame": cpp["us_per_frame"],
+                        "h2d_bytes_per_step": cpp["h2d_bytes_per_frame"], "d2h_bytes_per_step": cpp["d2h_bytes_per_frame"],
+                        "finite": cpp["finite"], "cpp_mirror": cpp, "cpp_mirror_one_call_per_dye": cpp_unbatched})
+        else:
+            out["cpp_mirror"] = cpp
+    # the Python mirror (what the tests drive)
     s = Scene(fb.FluidSim, fb.DensitySim, w, h, n_dyes=wl.dyes)
     rgb = np.empty((h, w, 3), np.float32)
     four = len(s.dyes) == 4
@@ -705,27 +742,29 @@ def run_e2e_frames(args, fb, torch, wl):
         s.frame(DT, wl.visc, wl.diff)
         if four:
             c, m, y, k = (d._h for d in s.dyes)
-            _lib.check(L.fruid_density_colors(c, m, y, k, _lib.ptr(rgb.reshape(h, 3 * w))))
+            _lib.check(L.fruid_density_colors(c, m, y, k, rgb.reshape(h, 3 * w)))
         else:
             s.dyes[0].density().numpy()
-
-    n = args.steps if args.steps is not None else (wl.steps or 100)
-    n = max(2, min(n, 200))
+    npy = max(2, min(n, 200))
     for _ in range(3):
         frame()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(n):
+    for _ in range(npy):
         frame()
     torch.cuda.synchronize()
     sec = time.perf_counter() - t0
-    return {"value": w * h * n / sec, "unit": "cell-steps/s", "h2d_bytes_per_step": 2 * 4,
-            "d2h_bytes_per_step": (w * h * 3 * 4) if four else w * h * 4, "steps": n, "us_per_frame": sec / n * 1e6,
-            "finite": bool(np.isfinite(rgb).all()) if four else True,
-            "note": "crate-API mirror, the literal main.rs:94-118 frame: uv_mut()[pos] = .. (2 cells, forwarded as injections), "
-                    "density_mut().fill(0) on every dye (device-side fill, nothing uploaded), FluidSim::step, the dyes' "
-                    "step(sim.uv(), ..) batched on the device-resident velocity, then the frame's RGB (device draw_density "
-                    "colour map) copied to the host; wall clock per frame, synchronous like the viewer's loop"}
+    out["python_mirror_us_per_frame"] = sec / npy * 1e6
+    if "value" not in out:  # (not the four-dye scene: only the Python mirror ran)
+        out.update({"value": w * h * npy / sec, "us_per_frame": sec / npy * 1e6, "h2d_bytes_per_step": 8,
+                    "d2h_bytes_per_step": w * h * 4, "finite": True})
+    out["note"] = ("crate-API mirror, the literal main.rs:94-124 frame: uv_mut()[pos] = .. (2 cells, forwarded as injections), "
+                   "density_mut().data_mut().fill(0) on every dye (device-side fill, nothing uploaded), FluidSim::step, the dyes' "
+                   "step(sim.uv(), ..) on the device-resident velocity (batched; `cpp_mirror_one_call_per_dye` = one call per "
+                   "dye), then the frame's RGB (device draw_density colour map) copied to the host; wall clock per frame, "
+                   "synchronous like the viewer's loop; value = the compiled C++ mirror, python_mirror_us_per_frame = the same "
+                   "frame through fruid_b200.api")
+    return out
 
 
 def run_b200_multi(args, wl, fb, dist, rank, world, local):

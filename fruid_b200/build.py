@@ -86,12 +86,28 @@ def _compile(lib, extra, tag, verbose):
     return lib
 
 
+FRAME_E2E = os.path.join(LIBDIR, "frame_e2e")  # host program: the reference's frame loop through include/fruid.hpp
+
+
+def _build_frame_e2e():
+    src = os.path.join(HERE, "host", "frame_e2e.cpp")
+    hpp = os.path.join(HERE, "..", "include", "fruid.hpp")
+    if os.path.exists(FRAME_E2E) and all(os.path.getmtime(FRAME_E2E) >= os.path.getmtime(f) for f in (src, hpp, LIB)):
+        return
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-o", FRAME_E2E, src, "-L" + LIBDIR, "-lfruid_b200",
+                        "-Wl,-rpath,$ORIGIN"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+
+
 def build(force: bool = False, verbose: bool = False, debug: bool = True) -> str:
-    """Builds libfruid_b200.so and (debug=True) libfruid_b200_dbg.so, the FRUID_DEBUG twin the ordering tests load."""
+    """Builds libfruid_b200.so, (debug=True) libfruid_b200_dbg.so -- the FRUID_DEBUG twin the ordering tests load -- and
+    the host-side frame driver of the end-to-end bench."""
     if force or _stale(LIB):
         _compile(LIB, [], "", verbose)
     if debug and (force or _stale(DBG_LIB)):
         _compile(DBG_LIB, ["-DFRUID_DEBUG"], ".dbg", False)
+    _build_frame_e2e()
     return LIB
 
 

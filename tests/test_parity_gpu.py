@@ -464,6 +464,30 @@ def test_cpp_mirror_runs_a_step(fb, tmp_path):
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("batched", [1, 0])
+def test_cpp_mirror_frame_loop_vs_golden(fb, tmp_path, batched):
+    """The reference's frame loop (main.rs:36-52, 89-118) through the compiled C++ mirror of the crate API
+    (include/fruid.hpp, driven by fruid_b200/host/frame_e2e.cpp): single-cell uv_mut() writes forwarded as injections,
+    data_mut().fill(0) performed on the device, c.step(sim.uv(), ..) on the device-resident velocity.  Six frames at
+    64 x 48 against the oracle's golden fields, bit for bit; and the mirror must not move a whole field over PCIe."""
+    import subprocess
+    from fruid_b200.build import FRAME_E2E
+    g = np.load(os.path.join(GOLD, "scene_64x48_f6.npz"))
+    w, h = 64, 48
+    dump = tmp_path / "fields.bin"
+    r = subprocess.run([FRAME_E2E, str(w), str(h), "6", "0", str(batched), str(dump)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    raw = np.fromfile(dump, np.float32).reshape(12, h, w)
+    # frame_e2e places the dyes like main.rs:43-46 (c, k, m, y positions) and dumps c, m, y, k: Scene's order
+    names = ["u", "v", "u_prev", "v_prev"] + [f"{n}{i}" for i in range(4) for n in ("dens", "dens_prev")]
+    for a, k in zip(raw, names):
+        assert_bits(a, g[k], k)
+    # per frame: 2 injected cells up, the RGB frame down, nothing else
+    assert info["h2d_bytes_per_frame"] == 8 and info["injects_per_frame"] == 2 and info["device_fills_per_frame"] == 4
+    assert info["d2h_bytes_per_frame"] == w * h * 3 * 4
+
+
 def test_launch_counter_counts_kernels(fb):
     sim = fb.FluidSim(300, 200)
     sim.set_fused_sweeps(10)
