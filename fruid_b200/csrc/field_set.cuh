@@ -77,6 +77,20 @@ struct FieldSet {
     bool up_pending[4] = {false, false, false, false};
     float* dl_stage = nullptr;
     cudaEvent_t dl_snap = nullptr, dl_done = nullptr;                 // snapshot taken (compute) / downloaded (copy)
+    // Output buffer of the draw_* entry points, kept between calls: a stream-ordered allocation per frame would be
+    // returned to the OS at every synchronisation (default pool threshold) and cost ~0.4 ms per call to get back.
+    float* draw_buf = nullptr;
+    size_t draw_bytes = 0;
+    float* vel_stage[2] = {nullptr, nullptr};  // fruid_density_step_host: device copies of host-side (u, v)
+    int draw_buffer(size_t bytes, float** out) {
+        if (bytes > draw_bytes) {
+            if (draw_buf) { CU(cudaStreamSynchronize(stream)); CU(cudaFree(draw_buf)); draw_buf = nullptr; draw_bytes = 0; }
+            CU(cudaMalloc(&draw_buf, bytes));
+            draw_bytes = bytes;
+        }
+        *out = draw_buf;
+        return 0;
+    }
     // Host mirrors (fruid_fluid_bind_mirror): the caller's arrays that shadow u and v.  A mirror is current while
     // mirror_epoch == dev_epoch, i.e. it was downloaded after the last change of the device fields; then
     // fruid_density_step_host(d, u, v, ..) with exactly these pointers can use the device-resident velocity.
@@ -171,6 +185,8 @@ struct FieldSet {
             if (up_used[i]) cudaEventDestroy(up_used[i]);
         }
         if (dl_stage) cudaFree(dl_stage);
+        if (draw_buf) cudaFree(draw_buf);
+        for (float* p : vel_stage) if (p) cudaFree(p);
         if (dl_snap) cudaEventDestroy(dl_snap);
         if (dl_done) cudaEventDestroy(dl_done);
         if (copy_stream) cudaStreamDestroy(copy_stream);

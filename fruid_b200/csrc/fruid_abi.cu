@@ -448,18 +448,20 @@ extern "C" int fruid_density_step_host(fruid_density_t* d, const float* u, const
     }
     g_velocity_uploads.fetch_add(1);
     if (s.is_slab()) return fail(FRUID_ERR_BAD_ARG, "slab-decomposed density needs a device-resident velocity (fruid_density_step_dev)");
+    // staging fields for the uploaded velocity, kept with the handle (two stream-ordered allocations per call would
+    // be handed back to the OS at every synchronisation)
     const size_t bytes = s.g.pitch * (size_t)s.g.h * sizeof(float);
-    float *du = nullptr, *dv = nullptr;
-    CU(cudaMallocAsync(&du, bytes, s.stream));
-    CU(cudaMallocAsync(&dv, bytes, s.stream));
+    for (int k = 0; k < 2; ++k)
+        if (!s.vel_stage[k]) {
+            CU(cudaMalloc(&s.vel_stage[k], bytes));
+            CU(cudaMemsetAsync(s.vel_stage[k], 0, bytes, s.stream));  // the row padding stays zero
+        }
+    float *du = s.vel_stage[0], *dv = s.vel_stage[1];
     const size_t rb = (size_t)s.g.w * sizeof(float);
     CU(cudaMemcpy2DAsync(du, s.g.pitch * sizeof(float), u, rb, rb, (size_t)s.g.h, cudaMemcpyHostToDevice, s.stream));
     CU(cudaMemcpy2DAsync(dv, s.g.pitch * sizeof(float), v, rb, rb, (size_t)s.g.h, cudaMemcpyHostToDevice, s.stream));
-    int r = op_dens_step(s.buf[0], s.buf[1], du, dv, s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream);
-    cudaFreeAsync(du, s.stream);
-    cudaFreeAsync(dv, s.stream);
-    TRY(r);
-    CU(cudaStreamSynchronize(s.stream));
+    TRY(op_dens_step(s.buf[0], s.buf[1], du, dv, s.buf[2], s.buf[3], s.g, diff, dt, s.iters, s.fused, s.stream));
+    CU(cudaStreamSynchronize(s.stream));  // the caller's (possibly pageable) arrays may be reused right away
     return 0;
 }
 extern "C" void* fruid_density_stream(fruid_density_t* d) { return d ? (void*)d->s.stream : nullptr; }
@@ -484,7 +486,7 @@ static int draw_density_impl(fruid_density_t* c, fruid_density_t* m, fruid_densi
     const size_t per_cell = verts ? 24 : 3;
     const size_t bytes = (size_t)S.g.w * S.g.h * per_cell * sizeof(float);
     float* dev = nullptr;
-    CU(cudaMallocAsync(&dev, bytes, S.stream));
+    TRY(S.draw_buffer(bytes, &dev));
     const dim3 grid((S.g.w + 31) / 32, (S.g.h + 31) / 32), block(32, 8);
     const float cw = 2.0f / (float)S.g.w, ch = 2.0f / (float)S.g.h;  // main.rs:147-148
     if (verts)
@@ -492,7 +494,6 @@ static int draw_density_impl(fruid_density_t* c, fruid_density_t* m, fruid_densi
     else
         LAUNCH("k_draw_density_rgb", S.stream, (k_draw_density<false><<<grid, block, 0, S.stream>>>(c->s.buf[0], m->s.buf[0], y->s.buf[0], k->s.buf[0], S.g, z, cw, ch, dev)));
     CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, S.stream));
-    CU(cudaFreeAsync(dev, S.stream));
     CU(cudaStreamSynchronize(S.stream));
     return 0;
 }
@@ -513,12 +514,11 @@ extern "C" int fruid_draw_velocity_lines(fruid_fluid_t* f, float z, float* host_
     if (S.is_slab()) return fail(FRUID_ERR_BAD_ARG, "draw_velocity_lines needs a whole single-GPU field");
     const size_t bytes = (size_t)S.g.w * S.g.h * 12 * sizeof(float);
     float* dev = nullptr;
-    CU(cudaMallocAsync(&dev, bytes, S.stream));
+    TRY(S.draw_buffer(bytes, &dev));
     const dim3 grid((S.g.w + 31) / 32, (S.g.h + 31) / 32), block(32, 8);
     const float cw = 2.0f / (float)S.g.w, ch = 2.0f / (float)S.g.h;  // main.rs:186-187
     LAUNCH("k_draw_velocity_lines", S.stream, (k_draw_velocity_lines<<<grid, block, 0, S.stream>>>(S.buf[0], S.buf[1], S.g, z, cw, ch, dev)));
     CU(cudaMemcpyAsync(host_vertices, dev, bytes, cudaMemcpyDeviceToHost, S.stream));
-    CU(cudaFreeAsync(dev, S.stream));
     CU(cudaStreamSynchronize(S.stream));
     return 0;
 }
