@@ -50,6 +50,45 @@ struct StepGraph {
     }
 };
 static bool g_graphs_enabled = true;
+// Alternative halo exchange on the copy engines + stream memory operations (cuStreamWriteValue32 / cuStreamWaitValue32,
+// resolved through the runtime's driver entry points like the tensor-map encoder): FRUID_B200_SLAB_EXCHANGE=ce.  Same
+// protocol and the same bits as the exchange kernel, but measured SLOWER on 2 GPUs (1.251 vs 1.196 ms per 4096 x 8192
+// step: sixteen small in-stream copies per exchange cost more than the SM slots the kernel has to wait for), so the
+// default stays k_slab_pull.
+struct StreamMemOps {
+    typedef CUresult (*PFN_write32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    typedef CUresult (*PFN_wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    PFN_write32 write32 = nullptr;
+    PFN_wait32 wait32 = nullptr;
+    bool ok = false;
+};
+static const StreamMemOps& stream_mem_ops() {
+    static StreamMemOps M;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *pw = nullptr, *pq = nullptr;
+        cudaDriverEntryPointQueryResult q1, q2;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &pw, cudaEnableDefault, &q1) == cudaSuccess && q1 == cudaDriverEntryPointSuccess &&
+            cudaGetDriverEntryPoint("cuStreamWaitValue32", &pq, cudaEnableDefault, &q2) == cudaSuccess && q2 == cudaDriverEntryPointSuccess) {
+            M.write32 = reinterpret_cast<StreamMemOps::PFN_write32>(pw);
+            M.wait32 = reinterpret_cast<StreamMemOps::PFN_wait32>(pq);
+            M.ok = M.write32 && M.wait32;
+        } else {
+            cudaGetLastError();
+        }
+    });
+    return M;
+}
+static std::atomic<uint64_t> g_exchanges_on_copy_engines{0};
+static int g_slab_exchange_mode = -1;  // -1 = not decided yet, 0 = kernel, 1 = copy engines
+static bool slab_exchange_on_copy_engines() {
+    if (g_slab_exchange_mode < 0) {
+        const char* e = getenv("FRUID_B200_SLAB_EXCHANGE");
+        g_slab_exchange_mode = (e && strcmp(e, "ce") == 0 && stream_mem_ops().ok) ? 1 : 0;
+    }
+    return g_slab_exchange_mode == 1;
+}
+
 // Process-unique handle ids: a graph remembers the ids (not the host addresses) of the handles it was captured
 // with, so a handle that malloc places at the address of a destroyed one can never replay the dead handle's graph.
 static std::atomic<uint64_t> g_next_uid{1};
@@ -380,6 +419,37 @@ struct FieldSet {
             ++slot;
         }
         A.njobs = nj;
+        if (slab_exchange_on_copy_engines()) {
+            // The same single-handshake protocol as k_slab_pull (outboxes alternating by event parity), carried by the
+            // copy engines and stream memory operations instead of a kernel: no SM has to be free for it (the
+            // persistent tile kernel of the other stream owns every SM's register file for ~85 us at a time).
+            const StreamMemOps& M = stream_mem_ops();
+            for (int j = 0; j < nj; ++j) {
+                const PullJob& J = A.job[j];
+                if (J.out_rows > 0)
+                    CU(cudaMemcpyAsync(J.outbox, J.mine, (size_t)J.out_rows * g.pitch * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+            }
+            for (int d = 0; d < 2; ++d)   // announce: my outbox[par] holds event A.event (prior copies are flushed first)
+                if (A.nbr[d] >= 0 && M.write32(stream, (CUdeviceptr)&A.peer[d]->ready[me], (cuuint32_t)A.event, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
+                    return fail(FRUID_ERR_CUDA, "cuStreamWriteValue32 failed (halo exchange)");
+            for (int d = 0; d < 2; ++d) {
+                if (A.nbr[d] < 0) continue;
+                if (M.wait32(stream, (CUdeviceptr)&A.mine->ready[A.nbr[d]], (cuuint32_t)A.event, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                    return fail(FRUID_ERR_CUDA, "cuStreamWaitValue32 failed (halo exchange)");
+                for (int j = d; j < nj; j += 2) {
+                    const PullJob& J = A.job[j];
+                    if (J.in_rows > 0)
+                        CU(cudaMemcpyAsync(J.dst, J.src, (size_t)J.in_rows * g.pitch * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+                }
+            }
+            if (wait_adv_event > 0)
+                for (int r = 0; r < slab.world; ++r)
+                    if (r != me && M.wait32(stream, (CUdeviceptr)&A.mine->adv_done[r], (cuuint32_t)wait_adv_event, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                        return fail(FRUID_ERR_CUDA, "cuStreamWaitValue32 failed (advect epoch)");
+            pdl_chain_break(stream);
+            g_exchanges_on_copy_engines.fetch_add(1, std::memory_order_relaxed);
+            return 0;
+        }
         // enough CTAs to keep ~2-3 MB in flight over NVLink for wide grids, one pass for narrow ones
         const int ctas = (int)std::min<size_t>(64, std::max<size_t>(8, (g.pitch * SLAB_HALO / 4 + 1023) / 1024));
         LAUNCH("k_slab_pull", stream, (k_slab_pull<<<dim3(ctas, nj), 256, 0, stream>>>(A)));
