@@ -27,6 +27,9 @@ ap.add_argument("--h", type=int, default=1536)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--cfl", type=float, default=40.0)
 ap.add_argument("--visc", type=float, default=1e-6)
+ap.add_argument("--one-device", action="store_true",
+                help="all ranks share cuda:0 (CUDA IPC between processes on one device; gloo instead of NCCL for the handle "
+                     "exchange): lets a single-GPU box check the slab kernels, time-sliced and therefore slow")
 ap.add_argument("--frame-inputs", action="store_true",
                 help="between steps write sources like the reference's frame loop (main.rs:98-108): two velocity cells next "
                      "to a slab cut, dens_prev filled with 0 plus one dye cell -- host writes while other ranks may still "
@@ -34,8 +37,13 @@ ap.add_argument("--frame-inputs", action="store_true",
 args = ap.parse_args()
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+if args.one_device:
+    local = 0
 torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+if args.one_device:
+    dist.init_process_group("gloo")
+else:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 w, h = args.w, args.h
 DT = bench.DT
 sim = SlabFluidSim(w, h, rank, world)
@@ -109,7 +117,7 @@ if rank == 0:
         print(f"{name:10s}: {bad} mismatching cells of {got.size}  absmax {np.abs(ref[k]).max():.4g} {list(rows)}")
         ok &= bad == 0
     print("MULTI-GPU PARITY", "OK" if ok else "FAILED", f"world={world} grid={w}x{h} steps={args.steps} cfl={args.cfl}")
-flag = torch.tensor([1 if ok else 0], device="cuda")
+flag = torch.tensor([1 if ok else 0], device="cpu" if args.one_device else "cuda")
 dist.broadcast(flag, 0)
 dist.destroy_process_group()
 sys.exit(0 if int(flag.item()) else 1)
