@@ -68,6 +68,7 @@ SIGNATURES = {
     "fruid_set_tile_config": [_i, _i, _i],
     "fruid_debug_tile_plan": [_sz, _sz, _i, _i, _vp],
     "fruid_set_launch_overlap": [_i],
+    "fruid_set_advect_tile": [_i],
     "fruid_debug_set_schedule": [_i],
     "fruid_debug_set_tail_delay": [_i],
     "fruid_debug_recip_mode": [_f, _vp, _vp],

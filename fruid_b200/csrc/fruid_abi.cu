@@ -107,9 +107,12 @@ namespace { struct PdlEnv { PdlEnv() {
     if (const char* e = getenv("FRUID_B200_PDL_UNCHAINED")) g_pdl.unsafe = atoi(e) != 0;
     if (const char* e = getenv("FRUID_B200_VEL_FORK")) g_vel_fork = atoi(e) != 0;
     if (const char* e = getenv("FRUID_B200_DENS_OVERLAP")) g_dens_overlap = atoi(e) != 0;
+    if (const char* e = getenv("FRUID_B200_ADVECT_TILE")) g_advect_tile.store(atoi(e));
 } } g_pdl_env; }
 // Tuning / debugging knob: programmatic dependent launch between the kernels of a step (default on).
 extern "C" int fruid_set_launch_overlap(int on) { g_pdl.enabled = on != 0; g_cfg_epoch.fetch_add(1); return 0; }
+// Tuning knob: advect kernel on one GPU (0 = global gathers, 1 = shared-memory window, -1 = by grid size).
+extern "C" int fruid_set_advect_tile(int mode) { g_advect_tile.store(mode < 0 ? -1 : (mode != 0)); g_cfg_epoch.fetch_add(1); return 0; }
 // Tuning / debugging knob: replay steps as CUDA graphs (default on).
 extern "C" int fruid_set_graphs_enabled(int on) { g_graphs_enabled = on != 0; g_cfg_epoch.fetch_add(1); return 0; }
 // Debug knobs of the ordering tests.  bit 0: density diffuse beside the velocity step (default on), bit 1: u / v

@@ -102,28 +102,28 @@ static PFN_encodeTiled get_encode_tiled() {
 }
 
 struct TmKey {
-    const void* p; size_t pitch; int h; int th;
-    bool operator==(const TmKey& o) const { return p == o.p && pitch == o.pitch && h == o.h && th == o.th; }
+    const void* p; size_t pitch; int h; int th; int tw;
+    bool operator==(const TmKey& o) const { return p == o.p && pitch == o.pitch && h == o.h && th == o.th && tw == o.tw; }
 };
 struct TmKeyHash {
     size_t operator()(const TmKey& k) const {
-        return std::hash<const void*>()(k.p) ^ (k.pitch * 1315423911u) ^ ((size_t)k.h << 20) ^ (size_t)k.th;
+        return std::hash<const void*>()(k.p) ^ (k.pitch * 1315423911u) ^ ((size_t)k.h << 20) ^ (size_t)k.th ^ ((size_t)k.tw << 10);
     }
 };
 static std::mutex g_tm_mu;
 static std::unordered_map<TmKey, CUtensorMap, TmKeyHash> g_tm_cache;
 
-// Tensor map of a field for (128 x th) boxes.  Returns 0 or -4 (CUDA error).
-static int tile_tensor_map(const float* base, size_t pitch, int h, int th, CUtensorMap* out) {
+// Tensor map of a field for (tw x th) boxes, zero fill outside.  Returns 0 or -4 (CUDA error).
+static int field_tensor_map(const float* base, size_t pitch, int h, int tw, int th, CUtensorMap* out) {
     std::lock_guard<std::mutex> lk(g_tm_mu);
-    const TmKey key{base, pitch, h, th};
+    const TmKey key{base, pitch, h, th, tw};
     auto it = g_tm_cache.find(key);
     if (it != g_tm_cache.end()) { *out = it->second; return 0; }
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return -4;
     const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)h};
     const cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
-    const cuuint32_t box[2] = {128u, (cuuint32_t)th};
+    const cuuint32_t box[2] = {(cuuint32_t)tw, (cuuint32_t)th};
     const cuuint32_t estr[2] = {1u, 1u};
     CUtensorMap tm;
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
@@ -134,6 +134,9 @@ static int tile_tensor_map(const float* base, size_t pitch, int h, int th, CUten
     g_tm_cache.emplace(key, tm);
     *out = tm;
     return 0;
+}
+static inline int tile_tensor_map(const float* base, size_t pitch, int h, int th, CUtensorMap* out) {
+    return field_tensor_map(base, pitch, h, 128, th, out);  // the (128 x th) boxes of the fused Jacobi kernel
 }
 
 // Per-stream scheduler words (zeroed once; every launch leaves them zero again).

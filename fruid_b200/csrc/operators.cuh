@@ -8,6 +8,7 @@
 #include "kernels_serial.cuh"
 #include "kernels_vec.cuh"
 #include "jacobi_tile.cuh"
+#include "advect_tile.cuh"
 #include "slab_comm.cuh"
 
 using namespace fruid;
@@ -132,6 +133,16 @@ static int op_add_source_diffuse(int b, float*& x, float* x0, float*& scratch, f
     return op_lin_solve(b, x, x0, scratch, g, a, c, iters, fused, st, false, true, dt, z_tmp);
 }
 
+// Which advect kernel runs on one GPU (fruid_set_advect_tile): 0 = k_advect4 (global gathers), 1 = k_advect_tile
+// (gathered fields staged in shared memory), -1 = by size: the tiled kernel from ~1.5 M cells up -- it gives a thread
+// 16 cells instead of 4, which only pays once there are several blocks per SM.
+static std::atomic<int> g_advect_tile{-1};
+static inline bool advect_use_tile(const Geom& g) {
+    const int m = g_advect_tile.load(std::memory_order_relaxed);
+    if (m >= 0) return m != 0;
+    return (size_t)g.w * (size_t)g.h >= (size_t)1200 * 1200;
+}
+
 // advect, src/lib.rs:84-126, for 1..4 fields sharing the back-trace (slab mode: 1 or 2).  `tab` (slab mode) says where
 // the rows of the gathered fields live on the other ranks; d0[] must then be indexed by GLOBAL row
 // and [ly0, ly1) are the local rows to produce (default: every interior row).
@@ -160,7 +171,21 @@ static int op_advect(int nf, float* const* d, const float* const* d0, const int*
 #define FRUID_ADVECT(NF, PASS, name) \
     LAUNCH(name, st, launch_pdl(PASS != 2, k_advect4<NF, PASS>, (PASS == 2 ? dim3(296) : grid1), vec_block(), 0, st, a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, T))
     if (nf < 1 || nf > ADVECT_MAX_FIELDS || (multi && nf > 2)) return fail(FRUID_ERR_BAD_ARG, "advect: unsupported field count %d", nf);
-    if (!multi) {
+    if (!multi && ly0 == 1 && ly1 == g.h - 1 && advect_use_tile(g)) {
+        const bool self = (nf == 2 && d0[0] == u && d0[1] == v);  // lib.rs:204-205
+        int r;
+        prof_pre(st);
+        switch (nf) {
+            case 1: r = advect_tile_launch<1, false>(a, u, v, g, dt0, dt1, xmax, ymax, st); break;
+            case 2: r = self ? advect_tile_launch<2, true>(a, u, v, g, dt0, dt1, xmax, ymax, st)
+                             : advect_tile_launch<2, false>(a, u, v, g, dt0, dt1, xmax, ymax, st); break;
+            case 3: r = advect_tile_launch<3, false>(a, u, v, g, dt0, dt1, xmax, ymax, st); break;
+            default: r = advect_tile_launch<4, false>(a, u, v, g, dt0, dt1, xmax, ymax, st); break;
+        }
+        if (r == -4) return fail(FRUID_ERR_CUDA, "advect: no tensor map for the gathered fields");
+        static const char* const names[] = {"", "k_advect_tile_x1", "k_advect_tile_x2", "k_advect_tile_x3", "k_advect_tile_x4"};
+        TRY(launched(names[nf], st));
+    } else if (!multi) {
         switch (nf) {
             case 1: FRUID_ADVECT(1, 0, "k_advect4x1"); break;
             case 2: FRUID_ADVECT(2, 0, "k_advect4x2"); break;

@@ -86,6 +86,12 @@ int fruid_set_graphs_enabled(int on);
  * cannot change).  Default on (environment FRUID_B200_LAUNCH_OVERLAP=0 turns it off at load). */
 int fruid_set_launch_overlap(int on);
 
+/* Tuning knob: which advect kernel a single-GPU handle uses.  1 = the gathered fields are staged in shared memory
+ * (TMA window of 144 x 40 cells per 128 x 32 block; cells whose back-trace leaves the window gather from global
+ * memory), 0 = every tap is a global load, -1 (default) = by grid size (shared-memory window from ~1.5 M cells up;
+ * environment FRUID_B200_ADVECT_TILE sets it at load).  Results never change. */
+int fruid_set_advect_tile(int mode);
+
 /* Debug knobs of the ordering tests (tests/test_ordering_gpu.py).  fruid_debug_set_schedule: bit 0 = density
  * add_source + diffuse beside the velocity step still in flight, bit 1 = u / v diffuse on two streams, bit 2 = the
  * round-1 launch attribution (programmatic attribute on every launch, even straight after a graph launch or an

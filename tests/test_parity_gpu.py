@@ -89,10 +89,19 @@ def test_diffuse(fb, O, w, h, diff):
     assert_bits(x, xo)
 
 
+@pytest.fixture(params=[0, 1], ids=["gather", "window"])
+def advect_kernel(request, fb):
+    """Both single-GPU advect kernels: k_advect4 (global gathers) and k_advect_tile (shared-memory window); the
+    library picks by grid size unless pinned."""
+    fb._lib.check(fb._lib.lib.fruid_set_advect_tile(request.param))
+    yield request.param
+    fb._lib.check(fb._lib.lib.fruid_set_advect_tile(-1))
+
+
 @pytest.mark.parametrize("w,h", SIZES + [(2, 5)])
 @pytest.mark.parametrize("b", [POS, NEGX, NEGY])
 @pytest.mark.parametrize("speed", [0.0, 0.5, 30.0, 4500.0])
-def test_advect(fb, O, w, h, b, speed):
+def test_advect(fb, O, w, h, b, speed, advect_kernel):
     rng = np.random.default_rng(6)
     d0, u, v = rand_field(rng, w, h), rand_field(rng, w, h, speed), rand_field(rng, w, h, speed)
     d = rand_field(rng, w, h)
@@ -102,7 +111,53 @@ def test_advect(fb, O, w, h, b, speed):
     assert_bits(d, do)
 
 
-def test_advect_aliased_like_velocity_self_advection(fb, O):
+@pytest.mark.parametrize("w,h", [(130, 70), (700, 300), (1031, 517)])
+@pytest.mark.parametrize("cells", [0.7, 3.0, 9.0])
+def test_advect_window_and_gather_taps_mix(fb, O, w, h, cells, advect_kernel):
+    """Displacements of `cells` grid cells (standard deviation): the 8-column / 4-row margin of the shared-memory window
+    holds some back-traces and not others, inside one block and one warp; block rows/columns that end at the border."""
+    rng = np.random.default_rng(w + h)
+    dt = 0.1
+    u = rand_field(rng, w, h, cells / (dt * (w - 2)))
+    v = rand_field(rng, w, h, cells / (dt * (h - 2)))
+    d0, d = rand_field(rng, w, h), rand_field(rng, w, h)
+    do = d.copy()
+    fb.ops.advect(NEGY, d, d0, u, v, dt)
+    O.fruid_oracle_advect(NEGY, do, d0, u, v, w, h, dt, 1)
+    assert_bits(d, do)
+
+
+@pytest.mark.parametrize("w,h,visc,n", [(300, 140, 0.0, 1), (420, 333, 1e-5, 3), (515, 260, 0.0, 4)])
+def test_scene_steps_with_either_advect_kernel(fb, oracle_mod, w, h, visc, n, advect_kernel):
+    """Whole steps (velocity self-advection: the gathered fields are the advecting velocity, lib.rs:204-205; n dyes
+    advected by one launch, main.rs:114-118) with the advect kernel pinned."""
+    rng = np.random.default_rng(w * 3 + n)
+    init = [rand_field(rng, w, h, 0.2) for _ in range(4)]
+    sim, of = fb.FluidSim(w, h), oracle_mod.Fluid(w, h)
+    _load_fluid(fb, sim, init)
+    for a, src in zip((of.u, of.v, of.u_prev, of.v_prev), init):
+        a[:] = src
+    dyes = [fb.DensitySim(w, h) for _ in range(n)]
+    odyes = [oracle_mod.Density(w, h) for _ in range(n)]
+    for d, od in zip(dyes, odyes):
+        a, b = rand_field(rng, w, h), rand_field(rng, w, h)
+        od.dens[:] = a
+        od.dens_prev[:] = b
+        fb._lib.check(fb._lib.lib.fruid_density_upload(d._h, 0, a))
+        fb._lib.check(fb._lib.lib.fruid_density_upload(d._h, 1, b))
+    for step in range(3):
+        sim.step(0.02, visc)
+        of.step(0.02, visc)
+        fb.DensitySim.step_all(dyes, sim.uv(), 0.02, visc)
+        for od in odyes:
+            od.step((of.u, of.v), 0.02, visc)
+    for g, want, nm in zip(_read_fluid(fb, sim, w, h), (of.u, of.v, of.u_prev, of.v_prev), ("u", "v", "u_prev", "v_prev")):
+        assert_bits(g, want, nm)
+    for i, (d, od) in enumerate(zip(dyes, odyes)):
+        assert_bits(d.density().numpy(), od.dens, f"dens{i}")
+
+
+def test_advect_aliased_like_velocity_self_advection(fb, O, advect_kernel):
     """lib.rs:204: advect(NegX, u, u0, u0, v0, dt) -- d0 aliases u."""
     w, h = 130, 70
     rng = np.random.default_rng(7)
@@ -113,7 +168,7 @@ def test_advect_aliased_like_velocity_self_advection(fb, O):
     assert_bits(d, do)
 
 
-def test_advect_special_values(fb, O):
+def test_advect_special_values(fb, O, advect_kernel):
     """NaN passes the clamps and casts to 0 (lib.rs:95-112); +-inf saturate at the clamps;
     -0.0 and denormals are preserved (no FTZ)."""
     w, h = 40, 24
