@@ -10,10 +10,10 @@
 //   * lane l of a warp owns columns l, l + 32, l + 64, l + 96 of four rows: the taps of neighbouring lanes are
 //     neighbouring words, one shared-memory wavefront per tap instruction, with the row stride of the window as an
 //     immediate offset (one address computation per cell for all taps of all fields);
-//   * a cell whose back-trace leaves the window (|displacement| larger than the margin: CFL > 4) takes the global
-//     gather of kernels_basic.cuh instead -- per cell, so results never depend on which path ran;
+//   * a thread whose four cells may trace back beyond the window (a displacement above 7 columns or 3 rows) gathers
+//     from global memory instead -- same taps, same arithmetic, so results never depend on which path ran;
 //   * velocity self-advection (lib.rs:204-205: the gathered fields ARE the advecting velocity) reads the cell's own
-//     velocity from the window too (SELF), i.e. u0, v0 are read once;
+//     velocity from the window too, i.e. u0, v0 are read once; a density advect gets u, v as two more TMA boxes;
 //   * set_bnd (lib.rs:125) is folded into the stores; only blocks that touch the domain border pay for its tests.
 // Arithmetic is the scalar code of kernels_basic.cuh (backtrace(), mixf()): bit-identical to k_advect / k_advect4.
 #pragma once
@@ -30,6 +30,7 @@ constexpr int ADV_FIELD_FLOATS = ADV_WW * ADV_WH; // 5760 floats = 23040 B per f
 
 struct AdvectTileArgs {
     CUtensorMap tm[ADVECT_MAX_FIELDS];  // gathered fields d0[f]: dims (pitch, h), box (ADV_WW, ADV_WH)
+    CUtensorMap tm_u, tm_v;             // the advecting velocity, box (ADV_TW, ADV_TH) (UVT kernels only)
     AdvectArgs a;
     const float* u;
     const float* v;
@@ -37,22 +38,48 @@ struct AdvectTileArgs {
     float dt0, dt1, xmax, ymax;
 };
 
-template <int NF>
-constexpr size_t advect_tile_smem_bytes() { return (size_t)NF * ADV_FIELD_FLOATS * sizeof(float) + 16; }
+// Where a cell's own velocity comes from: the windows themselves (velocity self-advection), two more TMA boxes
+// (one or two gathered fields: everything arrives asynchronously, nothing waits on a register), or plain loads
+// (three or four dyes: the windows already fill the shared memory an SM can give two blocks).
+enum : int { ADV_UV_SELF = 0, ADV_UV_TMA = 1, ADV_UV_LDG = 2 };
+constexpr int ADV_UV_FLOATS = ADV_TW * ADV_TH;    // 4096 floats = 16 KiB per velocity component
+template <int NF, int UV>
+constexpr size_t advect_tile_smem_bytes() {
+    return ((size_t)NF * ADV_FIELD_FLOATS + (UV == ADV_UV_TMA ? 2 * ADV_UV_FLOATS : 0)) * sizeof(float) + 16;
+}
 
-template <int NF, bool SELF>
+// min / max that keep a NaN operand (FMNMX.NAN): `if (x < lo) x = lo; if (x > hi) x = hi;` of lib.rs:95-110 leaves
+// a NaN alone (both comparisons are false), exactly like these.
+__device__ __forceinline__ float max_keep_nan(float x, float lo) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float min_keep_nan(float x, float hi) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(hi));
+    return r;
+}
+
+template <int NF, int UV>
 __global__ void __launch_bounds__(256) k_advect_tile(const __grid_constant__ AdvectTileArgs A) {
     pdl_enter();
     extern __shared__ __align__(128) unsigned char adv_smem[];
+    constexpr uint32_t TX_BYTES = (uint32_t)((NF * ADV_FIELD_FLOATS + (UV == ADV_UV_TMA ? 2 * ADV_UV_FLOATS : 0)) * sizeof(float));
     float* const win = reinterpret_cast<float*>(adv_smem);
-    uint64_t* const mbar = reinterpret_cast<uint64_t*>(adv_smem + (size_t)NF * ADV_FIELD_FLOATS * sizeof(float));
+    float* const uvt = win + NF * ADV_FIELD_FLOATS;  // ADV_UV_TMA: u tile, then v tile
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(adv_smem + TX_BYTES);
     const Geom& g = A.g;
     const int bx0 = blockIdx.x * ADV_TW;           // first column of the block (column 0 is the border)
     const int by0 = 1 + blockIdx.y * ADV_TH;       // first (interior) row of the block
     const int wx0 = bx0 - ADV_MX, wy0 = by0 - ADV_MY;  // window origin
     if (threadIdx.x == 0) {
         mbar_init(mbar, 1);
-        mbar_expect_tx(mbar, (uint32_t)(NF * ADV_FIELD_FLOATS * sizeof(float)));
+        mbar_expect_tx(mbar, TX_BYTES);
+        if (UV == ADV_UV_TMA) {
+            tma_load_2d(uvt, &A.tm_u, bx0, by0, mbar);
+            tma_load_2d(uvt + ADV_UV_FLOATS, &A.tm_v, bx0, by0, mbar);
+        }
 #pragma unroll
         for (int f = 0; f < NF; ++f) tma_load_2d(win + f * ADV_FIELD_FLOATS, &A.tm[f], wx0, wy0, mbar);
     }
@@ -60,76 +87,144 @@ __global__ void __launch_bounds__(256) k_advect_tile(const __grid_constant__ Adv
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     // set_bnd tests only where the block touches the border (block-uniform)
     const bool edge = (bx0 == 0) || (bx0 + ADV_TW >= g.nx) || (by0 == 1) || (by0 + ADV_TH > g.ny);
+    const int i_first = bx0 + lane;                // my columns: i_first + 32 c
+    float fi[4];
+    bool col_ok[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        fi[c] = (float)(i_first + 32 * c);
+        col_ok[c] = (i_first + 32 * c >= 1) && (i_first + 32 * c <= g.nx);
+    }
+    const int jw = by0 + wi * 4;                   // my first row
+    const int nrows = min(4, g.ny + 1 - jw);       // warp-uniform
+    // Window word of tap (i0, j0) = j0*ADV_WW + i0 - wbase; the centre cell (i, j) likewise.
+    const int wbase = wy0 * ADV_WW + wx0;
+    const float dt0 = A.dt0, dt1 = A.dt1, xmax = A.xmax, ymax = A.ymax;
     mbar_wait(mbar, 0);
     dbg_tail_delay(wi);
 #pragma unroll 1
-    for (int rr = 0; rr < 4; ++rr) {
-        const int j = by0 + wi * 4 + rr;
-        if (j > g.ny) break;  // warp-uniform
-        const float* const wrow = win + (j - wy0) * ADV_WW + (lane + ADV_MX);
+    for (int rr = 0; rr < nrows; ++rr) {
+        const int j = jw + rr;
+        const float fj = (float)j;
+        const size_t krow = (size_t)j * g.pitch + (size_t)i_first;
         float uc[4], vc[4];
+        if (UV == ADV_UV_SELF) {
+            const float* const wrow = win + (j * ADV_WW + i_first - wbase);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int i = bx0 + lane + 32 * c;
-            if (SELF) {
-                uc[c] = wrow[32 * c];
-                vc[c] = wrow[32 * c + ADV_FIELD_FLOATS];
-            } else {
-                const bool in = (i >= 1 && i <= g.nx);
-                const size_t k = at(g, i, j);
-                uc[c] = in ? __ldg(A.u + k) : 0.f;
-                vc[c] = in ? __ldg(A.v + k) : 0.f;
+            for (int c = 0; c < 4; ++c) { uc[c] = wrow[32 * c]; vc[c] = wrow[32 * c + ADV_FIELD_FLOATS]; }
+        } else if (UV == ADV_UV_TMA) {
+            const float* const urow = uvt + (j - by0) * ADV_TW + lane;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { uc[c] = urow[32 * c]; vc[c] = urow[32 * c + ADV_UV_FLOATS]; }
+        } else {
+            const float* const urow = A.u + krow;
+            const float* const vrow = A.v + krow;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uc[c] = col_ok[c] ? __ldg(urow + 32 * c) : 0.f;
+                vc[c] = col_ok[c] ? __ldg(vrow + 32 * c) : 0.f;
             }
         }
+        // Displacements in cells (lib.rs:92-93).  |dt0*u| <= 7 and |dt1*v| <= 3 for all four cells puts every tap inside
+        // the window: x = i - dt0*u rounds monotonically, so i0 = trunc(clamped x) lies in [i-7, i+7] (the clamps of
+        // lib.rs:95-110 only move x towards the interior) and i0+1 <= i+8; rows likewise within [j-3, j+4].  The
+        // NaN-keeping max makes a NaN displacement fail the test.
+        float du[4], dv[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int i = bx0 + lane + 32 * c;
-            if (i < 1 || i > g.nx) continue;
-            const Trace t = backtrace(i, j, uc[c], vc[c], A.dt0, A.dt1, A.xmax, A.ymax);
-            const unsigned wx = (unsigned)(t.i0 - wx0), wy = (unsigned)(t.j0 - wy0);
-            float r[NF];
-            if (wx <= (unsigned)(ADV_WW - 2) && wy <= (unsigned)(ADV_WH - 2)) {  // taps (wx, wx+1) x (wy, wy+1) inside
-                const float* p = win + wy * ADV_WW + wx;
+        for (int c = 0; c < 4; ++c) { du[c] = fmul(dt0, uc[c]); dv[c] = fmul(dt1, vc[c]); }
+        const float mx = max_keep_nan(max_keep_nan(fabsf(du[0]), fabsf(du[1])), max_keep_nan(fabsf(du[2]), fabsf(du[3])));
+        const float my = max_keep_nan(max_keep_nan(fabsf(dv[0]), fabsf(dv[1])), max_keep_nan(fabsf(dv[2]), fabsf(dv[3])));
+        const bool near = (mx <= (float)(ADV_MX - 1)) && (my <= (float)(ADV_MY - 1));
+        Trace t[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {  // backtrace(), kernels_basic.cuh, with i and j already converted
+            float x = fsub(fi[c], du[c]);
+            float y = fsub(fj, dv[c]);
+            x = min_keep_nan(max_keep_nan(x, 0.5f), xmax);
+            y = min_keep_nan(max_keep_nan(y, 0.5f), ymax);
+            t[c].i0 = (int)__float2uint_rz(x);
+            t[c].j0 = (int)__float2uint_rz(y);
+            t[c].s1 = fsub(x, (float)t[c].i0);
+            t[c].t1 = fsub(y, (float)t[c].j0);
+        }
+        float r[NF][4];
+        if (near) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float* const p = win + (t[c].j0 * ADV_WW + t[c].i0 - wbase);
+                const float t0 = fsub(1.0f, t[c].t1), s0 = fsub(1.0f, t[c].s1);
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
                     const float a00 = p[f * ADV_FIELD_FLOATS], a10 = p[f * ADV_FIELD_FLOATS + 1];
                     const float a01 = p[f * ADV_FIELD_FLOATS + ADV_WW], a11 = p[f * ADV_FIELD_FLOATS + ADV_WW + 1];
-                    r[f] = mixf(mixf(a00, a01, t.t1), mixf(a10, a11, t.t1), t.s1);
+                    // mix(mix(a00, a01, t1), mix(a10, a11, t1), s1), lib.rs:80-82,118-121
+                    const float m0 = fadd(fmul(t0, a00), fmul(t[c].t1, a01));
+                    const float m1 = fadd(fmul(t0, a10), fmul(t[c].t1, a11));
+                    r[f][c] = fadd(fmul(s0, m0), fmul(t[c].s1, m1));
                 }
-            } else {
-#pragma unroll
-                for (int f = 0; f < NF; ++f) r[f] = gather(A.a.d0[f], g, t);
             }
+        } else {
+            // A back-trace may leave the window (CFL beyond the margins): this thread takes its four cells from global
+            // memory -- all loads first, then the arithmetic; taps are always inside the field (lib.rs:95-110), also
+            // for the columns outside the interior, whose results are never stored.
+            size_t q[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) q[c] = at(g, t[c].i0, t[c].j0);
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
-                if (edge) store_with_bnd(A.a.d[f], g, A.a.b[f], i, j, r[f]);
-                else A.a.d[f][at(g, i, j)] = r[f];
+                float a00[4], a10[4], a01[4], a11[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float* const p = A.a.d0[f] + q[c];
+                    a00[c] = __ldg(p); a10[c] = __ldg(p + 1); a01[c] = __ldg(p + g.pitch); a11[c] = __ldg(p + g.pitch + 1);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    r[f][c] = mixf(mixf(a00[c], a01[c], t[c].t1), mixf(a10[c], a11[c], t[c].t1), t[c].s1);
             }
+        }
+        if (!edge) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                float* const orow = A.a.d[f] + krow;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) orow[32 * c] = r[f][c];
+            }
+        } else {
+#pragma unroll
+            for (int f = 0; f < NF; ++f)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (col_ok[c]) store_with_bnd(A.a.d[f], g, A.a.b[f], i_first + 32 * c, j, r[f][c]);
         }
     }
 }
 
 // Tensor maps of the gathered fields + launch.  Returns a cudaError_t as int, or -4 when no tensor map can be made.
-template <int NF, bool SELF>
+template <int NF, int UV>
 static int advect_tile_launch(const AdvectArgs& a, const float* u, const float* v, const Geom& g, float dt0, float dt1,
                               float xmax, float ymax, cudaStream_t st) {
     AdvectTileArgs A;
     for (int f = 0; f < NF; ++f)
         if (int r = field_tensor_map(a.d0[f], g.pitch, g.h, ADV_WW, ADV_WH, &A.tm[f])) return r;
+    if (UV == ADV_UV_TMA) {
+        if (int r = field_tensor_map(u, g.pitch, g.h, ADV_TW, ADV_TH, &A.tm_u)) return r;
+        if (int r = field_tensor_map(v, g.pitch, g.h, ADV_TW, ADV_TH, &A.tm_v)) return r;
+    }
     A.a = a; A.u = u; A.v = v; A.g = g; A.dt0 = dt0; A.dt1 = dt1; A.xmax = xmax; A.ymax = ymax;
-    constexpr size_t smem = advect_tile_smem_bytes<NF>();
+    constexpr size_t smem = advect_tile_smem_bytes<NF, UV>();
     if (smem > 48 * 1024) {
         static std::atomic<uint64_t> attr_devices{0};
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
         if (!((attr_devices.load(std::memory_order_acquire) >> dev) & 1)) {
-            const cudaError_t e = cudaFuncSetAttribute(k_advect_tile<NF, SELF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            const cudaError_t e = cudaFuncSetAttribute(k_advect_tile<NF, UV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
             attr_devices.fetch_or(1ull << dev, std::memory_order_release);
         }
     }
     const dim3 grid((g.w + ADV_TW - 1) / ADV_TW, (g.ny + ADV_TH - 1) / ADV_TH);
-    return (int)launch_pdl(true, k_advect_tile<NF, SELF>, grid, dim3(256), smem, st, A);
+    return (int)launch_pdl(true, k_advect_tile<NF, UV>, grid, dim3(256), smem, st, A);
 }
 
 }  // namespace fruid

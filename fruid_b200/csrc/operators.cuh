@@ -176,11 +176,11 @@ static int op_advect(int nf, float* const* d, const float* const* d0, const int*
         int r;
         prof_pre(st);
         switch (nf) {
-            case 1: r = advect_tile_launch<1, false>(a, u, v, g, dt0, dt1, xmax, ymax, st); break;
-            case 2: r = self ? advect_tile_launch<2, true>(a, u, v, g, dt0, dt1, xmax, ymax, st)
-                             : advect_tile_launch<2, false>(a, u, v, g, dt0, dt1, xmax, ymax, st); break;
-            case 3: r = advect_tile_launch<3, false>(a, u, v, g, dt0, dt1, xmax, ymax, st); break;
-            default: r = advect_tile_launch<4, false>(a, u, v, g, dt0, dt1, xmax, ymax, st); break;
+            case 1: r = advect_tile_launch<1, ADV_UV_TMA>(a, u, v, g, dt0, dt1, xmax, ymax, st); break;
+            case 2: r = self ? advect_tile_launch<2, ADV_UV_SELF>(a, u, v, g, dt0, dt1, xmax, ymax, st)
+                             : advect_tile_launch<2, ADV_UV_TMA>(a, u, v, g, dt0, dt1, xmax, ymax, st); break;
+            case 3: r = advect_tile_launch<3, ADV_UV_LDG>(a, u, v, g, dt0, dt1, xmax, ymax, st); break;
+            default: r = advect_tile_launch<4, ADV_UV_LDG>(a, u, v, g, dt0, dt1, xmax, ymax, st); break;
         }
         if (r == -4) return fail(FRUID_ERR_CUDA, "advect: no tensor map for the gathered fields");
         static const char* const names[] = {"", "k_advect_tile_x1", "k_advect_tile_x2", "k_advect_tile_x3", "k_advect_tile_x4"};
