@@ -258,7 +258,7 @@ static int jacobi_tile_launch(float* out, const float* x, const float* x0, const
     int mode = MODE_GENERAL;
     A.c = c;
     if (c == 1.0f) {
-        mode = MODE_ONE;
+        mode = (a == 0.0f) ? MODE_ZEROA : MODE_ONE;
     } else {
         int e = 0;
         const float m = frexpf(c, &e);

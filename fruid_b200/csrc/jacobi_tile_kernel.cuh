@@ -31,6 +31,9 @@
 // with 1/c when c is a power of two (bit-identical: same real value, same rounding);
 // MODE_ONE drops it when c == 1; MODE_POISSON additionally drops the multiplication by
 // a == 1 (1*sum == sum bit-for-bit).  Otherwise a*sum is always computed (0*inf etc.).
+// MODE_ZEROA is c == 1 with a == +-0 (diffusion with diff = 0, the reference scene: main.rs:110-118): the product
+// a*sum is then EXACT (+-0, or NaN for an infinite or NaN sum), so fma(a, sum, x0) rounds the same real number as the
+// unfused x0 + a*sum and obeys the same signed-zero rules -- one packed FFMA2 instead of two multiplies and an add.
 // MODE_RECIP divides by a general c without the ~25-instruction IEEE division sequence: with the
 // reciprocal as a double-word (zh, zl), q = fma(v, zh, v*zl) is the correctly rounded v/c (division
 // by a constant with an FMA, Brisebarre-Muller-Raina 2004) -- for "almost all" c; the claim is not
@@ -48,7 +51,7 @@
 
 namespace fruid {
 
-enum : int { MODE_GENERAL = 0, MODE_POW2 = 1, MODE_ONE = 2, MODE_POISSON = 3, MODE_RECIP = 4, MODE_RECIP3 = 5 };
+enum : int { MODE_GENERAL = 0, MODE_POW2 = 1, MODE_ONE = 2, MODE_POISSON = 3, MODE_RECIP = 4, MODE_RECIP3 = 5, MODE_ZEROA = 6 };
 
 struct TileArgs {
     CUtensorMap tm_x0;  // 2-D map over x0: dims (pitch, h) f32, box (128, R*NW), zero OOB fill
@@ -108,6 +111,11 @@ __device__ __forceinline__ float4 jac_row(const float4 z, float t0, float t1, fl
     float2 s23 = __fadd2_rn(make_float2(t2, t3), make_float2(up.z, up.w));
     s01 = __fadd2_rn(s01, make_float2(dn.x, dn.y));
     s23 = __fadd2_rn(s23, make_float2(dn.z, dn.w));
+    if (MODE == MODE_ZEROA) {  // x0 + a*sum with an exact product: see the header
+        s01 = __ffma2_rn(make_float2(a, a), s01, make_float2(z.x, z.y));
+        s23 = __ffma2_rn(make_float2(a, a), s23, make_float2(z.z, z.w));
+        return make_float4(s01.x, s01.y, s23.x, s23.y);
+    }
     if (MODE != MODE_POISSON) {
         // a*sum (for a == 1 the product is the sum itself, bit for bit).  SCALAR multiplies on
         // purpose: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under
@@ -332,35 +340,48 @@ __device__ __forceinline__ void jacobi_tile_body(const TileArgs& A, int kx, int 
     const bool v2 = gx0 + 2 >= xlo && gx0 + 2 < xhi, v3 = gx0 + 3 >= xlo && gx0 + 3 < xhi;
     const bool vall = v0 && v1 && v2 && v3;
     if (!EDGE) {
-        // Interior tile: [xlo, xhi) = [ox+H, ox+128-H) with H even, so a lane stores its whole
-        // float4, its low or high half (8-byte aligned), or nothing.  One branch on the lane's
-        // mode outside the row loop; inside it only a predicated store per row.
-        const int lo = A.H - 4 * lane, hi = 128 - A.H - 4 * lane;  // my components [lo, hi) are stored
-        const int mode = (lo <= 0 && hi >= 4) ? 1 : (lo <= 0 && hi == 2) ? 2 : (lo == 2 && hi >= 4) ? 3 : 0;
-        const unsigned rlo = (unsigned)max(0, ylo - gyw), rcnt = (unsigned)max(0, min(R, yhi - gyw) - (int)rlo);
-        float* const o0 = A.out + (size_t)gyw * g.pitch + gx0;
-        float* const z0 = (A.fuse_src && A.z_out) ? A.z_out + (size_t)gyw * g.pitch + gx0 : nullptr;
+        // Interior tile: no tile edge is a domain edge, so the stored cells are the tile-local box [H, 128-H) x [H, TH-H)
+        // whatever the tile.  H is even: a lane stores its low half, its high half, both or nothing -- two predicated
+        // 8-byte stores per row, the same instruction stream in every lane.
+        const int c0 = A.H - 4 * lane, c1 = 128 - A.H - 4 * lane;  // my components [c0, c1) are stored
+        const bool slo = (c0 <= 0) && (c1 >= 2), shi = (c0 <= 2) && (c1 >= 4);
+        const int r0 = A.H - wi * R, r1 = TH - A.H - wi * R;        // my rows [r0, r1) are stored
         const size_t pitch = g.pitch;
-        if (mode == 1) {
+        float* o = A.out + (size_t)gyw * pitch + gx0;
+        float* zo = (A.fuse_src && A.z_out) ? A.z_out + (size_t)gyw * pitch + gx0 : nullptr;
+        if (r0 <= 0 && r1 >= R) {  // all my rows (warp-uniform; every warp but the first and last two of a tile)
+            if (slo && shi) {      // 26 of 32 lanes: whole float4s
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-                if ((unsigned)r - rlo < rcnt) *reinterpret_cast<float4*>(o0 + r * pitch) = xr[r];
-            if (z0) {
+                for (int r = 0; r < R; ++r, o += pitch) *reinterpret_cast<float4*>(o) = xr[r];
+                if (zo) {
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if ((unsigned)r - rlo < rcnt) *reinterpret_cast<float4*>(z0 + r * pitch) = z[r];
+                    for (int r = 0; r < R; ++r, zo += pitch) *reinterpret_cast<float4*>(zo) = z[r];
+                }
+            } else if (slo || shi) {
+                const int sh = shi ? 2 : 0;
+#pragma unroll
+                for (int r = 0; r < R; ++r, o += pitch)
+                    *reinterpret_cast<float2*>(o + sh) = shi ? make_float2(xr[r].z, xr[r].w) : make_float2(xr[r].x, xr[r].y);
+                if (zo) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r, zo += pitch)
+                        *reinterpret_cast<float2*>(zo + sh) = shi ? make_float2(z[r].z, z[r].w) : make_float2(z[r].x, z[r].y);
+                }
             }
-        } else if (mode != 0) {
-            const int sh = (mode == 3) ? 2 : 0;  // which half of the float4
+        } else if (r1 > 0 && r0 < R) {
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-                if ((unsigned)r - rlo < rcnt)
-                    *reinterpret_cast<float2*>(o0 + r * pitch + sh) = sh ? make_float2(xr[r].z, xr[r].w) : make_float2(xr[r].x, xr[r].y);
-            if (z0) {
+            for (int r = 0; r < R; ++r, o += pitch) {
+                if (r < r0 || r >= r1) continue;  // warp-uniform
+                if (slo) *reinterpret_cast<float2*>(o) = make_float2(xr[r].x, xr[r].y);
+                if (shi) *reinterpret_cast<float2*>(o + 2) = make_float2(xr[r].z, xr[r].w);
+            }
+            if (zo) {
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if ((unsigned)r - rlo < rcnt)
-                        *reinterpret_cast<float2*>(z0 + r * pitch + sh) = sh ? make_float2(z[r].z, z[r].w) : make_float2(z[r].x, z[r].y);
+                for (int r = 0; r < R; ++r, zo += pitch) {
+                    if (r < r0 || r >= r1) continue;
+                    if (slo) *reinterpret_cast<float2*>(zo) = make_float2(z[r].x, z[r].y);
+                    if (shi) *reinterpret_cast<float2*>(zo + 2) = make_float2(z[r].z, z[r].w);
+                }
             }
         }
         return;

@@ -35,6 +35,7 @@ template <int R, int NW>
 static int tile_launch_cfg(const TileArgs& A, int mode, int num_sms, bool pdl, cudaStream_t st) {
     if (mode == MODE_GENERAL) return tile_launch_mode<R, NW, MODE_GENERAL>(A, num_sms, pdl, st);
     if (mode == MODE_POW2) return tile_launch_mode<R, NW, MODE_POW2>(A, num_sms, pdl, st);
+    if (mode == MODE_ZEROA) return tile_launch_mode<R, NW, MODE_ZEROA>(A, num_sms, pdl, st);
     if (mode == MODE_POISSON) return tile_launch_mode<R, NW, MODE_POISSON>(A, num_sms, pdl, st);
     if (mode == MODE_RECIP) return tile_launch_mode<R, NW, MODE_RECIP>(A, num_sms, pdl, st);
     if (mode == MODE_RECIP3) return tile_launch_mode<R, NW, MODE_RECIP3>(A, num_sms, pdl, st);

@@ -209,6 +209,31 @@ def test_lin_solve_denormals_and_negative_zero(fb, O):
     assert_bits(x, xo)
 
 
+@pytest.mark.parametrize("a", [0.0, -0.0])
+@pytest.mark.parametrize("b", [POS, NEGX])
+def test_lin_solve_zero_a_signed_zeros_infinities_nans(fb, O, a, b):
+    """diffuse with diff = 0 (main.rs:110-118): x0 + a*sum with a = +-0.  The tile kernel fuses it into one FMA, which is
+    exact because the product is (+-0, or NaN for an infinite / NaN sum); signed zeros, infinities, NaNs, denormals
+    and huge values in x and x0 must come out as from the unfused reference expression."""
+    w, h = 300, 170
+    rng = np.random.default_rng(12)
+    x, x0 = rand_field(rng, w, h), rand_field(rng, w, h)
+    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-42, -1e-42, 3e38, -3e38, 1e-30], np.float32)
+    for arr in (x, x0):
+        ys, xs = rng.integers(0, h, 400), rng.integers(0, w, 400)
+        arr[ys, xs] = special[rng.integers(0, len(special), 400)]
+    x0[20:40, 30:90] = -0.0   # a block of negative zeros: -0 + (+0) = +0 but -0 + (-0) = -0
+    x[60:80, 100:200] *= -1.0
+    s = np.zeros((h, w), np.float32)
+    xo, so = x.copy(), s.copy()
+    with np.errstate(all="ignore"):
+        fb.ops.lin_solve(b, x, x0, s, a, 1.0, 20, 0)
+        O.fruid_oracle_lin_solve(b, xo, x0, so, w, h, a, 1.0, 20, 1)
+    assert_bits(x, xo)
+    both = ~(np.isnan(x) | np.isnan(xo))
+    assert np.array_equal(np.signbit(x[both]), np.signbit(xo[both]))
+
+
 # ---- whole steps through the handle API ----------------------------------------------------
 def _load_fluid(fb, sim, fields):
     for arr, field in zip(fields, (0, 1, 2, 3)):
