@@ -19,6 +19,7 @@
 #pragma once
 #include "jacobi_tile.cuh"
 #include "kernels_basic.cuh"
+#include "kernels_vec.cuh"
 
 namespace fruid {
 
@@ -36,7 +37,30 @@ struct AdvectTileArgs {
     const float* v;
     Geom g;
     float dt0, dt1, xmax, ymax;
+    int ly0, ly1;                       // LOCAL rows to produce: [1, h-1) on one GPU, the owned rows of a slab
 };
+
+// store_with_bnd (common.cuh) for a y-slab: the cell sits at LOCAL row ly, boundary logic uses its global row.
+__device__ __forceinline__ void store_with_bnd_rows(float* __restrict__ out, const Geom& g, int b, int i, int ly, float v) {
+    const size_t k = at(g, i, ly);
+    out[k] = v;
+    const int gy = ly + g.gy0;
+    const bool nxg = (b == B_NEGX), nyg = (b == B_NEGY);
+    const bool xl = (i == 1), xr = (i == g.nx), yt = (gy == 1), yb = (gy == g.ny);
+    if (xl | xr | yt | yb) {
+        const float vx = sgn(nxg, v), vy = sgn(nyg, v);
+        const size_t up = k - g.pitch, dn = k + g.pitch;
+        if (xl) out[k - 1] = vx;
+        if (xr) out[k + 1] = vx;
+        if (yt) out[up] = vy;
+        if (yb) out[dn] = vy;
+        const float c = fmul(0.5f, fadd(vy, vx));
+        if (xl && yt) out[up - 1] = c;
+        if (xl && yb) out[dn - 1] = c;
+        if (xr && yt) out[up + 1] = c;
+        if (xr && yb) out[dn + 1] = c;
+    }
+}
 
 // Where a cell's own velocity comes from: the windows themselves (velocity self-advection), two more TMA boxes
 // (one or two gathered fields: everything arrives asynchronously, nothing waits on a register), or plain loads
@@ -61,9 +85,15 @@ __device__ __forceinline__ float min_keep_nan(float x, float hi) {
     return r;
 }
 
-template <int NF, int UV>
-__global__ void __launch_bounds__(256) k_advect_tile(const __grid_constant__ AdvectTileArgs A) {
+// PASS 0: one GPU.  PASS 1: a y-slab (kernels_vec.cuh: k_advect4<NF, 1>) -- only quads of four aligned columns whose
+// eight tap rows are all owned by this rank are produced here; the others queue their 128 x 8 block of k_advect4's
+// geometry for its pass 2, which gathers them from the owners' memory.  A.a.d0[] is then indexed by GLOBAL row, the
+// windows and everything else by local row.
+template <int NF, int UV, int PASS>
+__global__ void __launch_bounds__(256) k_advect_tile(const __grid_constant__ AdvectTileArgs A, const __grid_constant__ SlabTable tab) {
     pdl_enter();
+    if (PASS == 1 && blockIdx.x == 0 && blockIdx.y == 0 && (int)threadIdx.x < tab.world)
+        st_release_sys(&tab.flags[threadIdx.x]->src_done[tab.me], tab.event);  // folded "src_done" broadcast, see k_advect4
     extern __shared__ __align__(128) unsigned char adv_smem[];
     constexpr uint32_t TX_BYTES = (uint32_t)((NF * ADV_FIELD_FLOATS + (UV == ADV_UV_TMA ? 2 * ADV_UV_FLOATS : 0)) * sizeof(float));
     float* const win = reinterpret_cast<float*>(adv_smem);
@@ -71,7 +101,7 @@ __global__ void __launch_bounds__(256) k_advect_tile(const __grid_constant__ Adv
     uint64_t* const mbar = reinterpret_cast<uint64_t*>(adv_smem + TX_BYTES);
     const Geom& g = A.g;
     const int bx0 = blockIdx.x * ADV_TW;           // first column of the block (column 0 is the border)
-    const int by0 = 1 + blockIdx.y * ADV_TH;       // first (interior) row of the block
+    const int by0 = A.ly0 + blockIdx.y * ADV_TH;   // first row of the block (local)
     const int wx0 = bx0 - ADV_MX, wy0 = by0 - ADV_MY;  // window origin
     if (threadIdx.x == 0) {
         mbar_init(mbar, 1);
@@ -86,7 +116,7 @@ __global__ void __launch_bounds__(256) k_advect_tile(const __grid_constant__ Adv
     __syncthreads();  // the barrier is initialised before anybody waits on it
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     // set_bnd tests only where the block touches the border (block-uniform)
-    const bool edge = (bx0 == 0) || (bx0 + ADV_TW >= g.nx) || (by0 == 1) || (by0 + ADV_TH > g.ny);
+    const bool edge = (bx0 == 0) || (bx0 + ADV_TW >= g.nx) || (by0 + g.gy0 == 1) || (by0 + g.gy0 + ADV_TH > g.ny);
     const int i_first = bx0 + lane;                // my columns: i_first + 32 c
     float fi[4];
     bool col_ok[4];
@@ -96,24 +126,24 @@ __global__ void __launch_bounds__(256) k_advect_tile(const __grid_constant__ Adv
         col_ok[c] = (i_first + 32 * c >= 1) && (i_first + 32 * c <= g.nx);
     }
     const int jw = by0 + wi * 4;                   // my first row
-    const int nrows = min(4, g.ny + 1 - jw);       // warp-uniform
-    // Window word of tap (i0, j0) = j0*ADV_WW + i0 - wbase; the centre cell (i, j) likewise.
-    const int wbase = wy0 * ADV_WW + wx0;
+    const int nrows = min(4, A.ly1 - jw);          // warp-uniform
+    // Window word of tap (i0, j0) = j0*ADV_WW + i0 - wbase (j0 a GLOBAL row); the centre cell (i, j) likewise.
+    const int wbase = (wy0 + g.gy0) * ADV_WW + wx0;
     const float dt0 = A.dt0, dt1 = A.dt1, xmax = A.xmax, ymax = A.ymax;
     mbar_wait(mbar, 0);
     dbg_tail_delay(wi);
 #pragma unroll 1
     for (int rr = 0; rr < nrows; ++rr) {
-        const int j = jw + rr;
+        const int jl = jw + rr, j = jl + g.gy0;    // local / global row
         const float fj = (float)j;
-        const size_t krow = (size_t)j * g.pitch + (size_t)i_first;
+        const size_t krow = (size_t)jl * g.pitch + (size_t)i_first;
         float uc[4], vc[4];
         if (UV == ADV_UV_SELF) {
             const float* const wrow = win + (j * ADV_WW + i_first - wbase);
 #pragma unroll
             for (int c = 0; c < 4; ++c) { uc[c] = wrow[32 * c]; vc[c] = wrow[32 * c + ADV_FIELD_FLOATS]; }
         } else if (UV == ADV_UV_TMA) {
-            const float* const urow = uvt + (j - by0) * ADV_TW + lane;
+            const float* const urow = uvt + (jl - by0) * ADV_TW + lane;
 #pragma unroll
             for (int c = 0; c < 4; ++c) { uc[c] = urow[32 * c]; vc[c] = urow[32 * c + ADV_UV_FLOATS]; }
         } else {
@@ -169,7 +199,11 @@ __global__ void __launch_bounds__(256) k_advect_tile(const __grid_constant__ Adv
             // for the columns outside the interior, whose results are never stored.
             size_t q[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) q[c] = at(g, t[c].i0, t[c].j0);
+            for (int c = 0; c < 4; ++c) {
+                q[c] = at(g, t[c].i0, t[c].j0);
+                // a slab holds only its own rows: taps elsewhere are pass 2's business, load something harmless instead
+                if (PASS == 1 && !((t[c].j0 >= tab.my_lo) && (t[c].j0 + 1 < tab.my_hi))) q[c] = (size_t)j * g.pitch;
+            }
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 float a00[4], a10[4], a01[4], a11[4];
@@ -183,48 +217,73 @@ __global__ void __launch_bounds__(256) k_advect_tile(const __grid_constant__ Adv
                     r[f][c] = mixf(mixf(a00[c], a01[c], t[c].t1), mixf(a10[c], a11[c], t[c].t1), t[c].s1);
             }
         }
-        if (!edge) {
+        bool own[4] = {true, true, true, true};
+        if (PASS == 1) {
+            // k_advect4's pass 2 decides per thread = per quad of aligned columns [4q, 4q+4) (all of them, border and
+            // padding columns of the field included) whether the quad's taps are all in rows this rank owns.
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const bool mine = (t[c].j0 >= tab.my_lo) && (t[c].j0 + 1 < tab.my_hi);
+                const unsigned quad = (__ballot_sync(0xffffffffu, mine) >> (lane & 28)) & 0xfu;
+                const bool counted = ((i_first + 32 * c) & ~3) < g.w;  // k_advect4 returns early for gx0 >= w
+                own[c] = (quad == 0xfu);
+                if (!own[c] && counted && (lane & 3) == 0) {  // queue the quad's block once
+                    const int bid = ((jl - A.ly0) >> 3) * tab.grid_x + (int)blockIdx.x;
+                    if (atomicExch(&tab.block_flag[bid], 1) == 0) tab.block_list[1 + atomicAdd(&tab.block_list[0], 1)] = bid;
+                }
+            }
+        }
+        if (!edge && PASS == 0) {
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 float* const orow = A.a.d[f] + krow;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) orow[32 * c] = r[f][c];
             }
+        } else if (!edge) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                float* const orow = A.a.d[f] + krow;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (own[c]) orow[32 * c] = r[f][c];
+            }
         } else {
 #pragma unroll
             for (int f = 0; f < NF; ++f)
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
-                    if (col_ok[c]) store_with_bnd(A.a.d[f], g, A.a.b[f], i_first + 32 * c, j, r[f][c]);
+                    if (col_ok[c] && own[c]) store_with_bnd_rows(A.a.d[f], g, A.a.b[f], i_first + 32 * c, jl, r[f][c]);
         }
     }
 }
 
 // Tensor maps of the gathered fields + launch.  Returns a cudaError_t as int, or -4 when no tensor map can be made.
-template <int NF, int UV>
+template <int NF, int UV, int PASS>
 static int advect_tile_launch(const AdvectArgs& a, const float* u, const float* v, const Geom& g, float dt0, float dt1,
-                              float xmax, float ymax, cudaStream_t st) {
+                              float xmax, float ymax, int ly0, int ly1, const SlabTable& tab, cudaStream_t st) {
     AdvectTileArgs A;
-    for (int f = 0; f < NF; ++f)
-        if (int r = field_tensor_map(a.d0[f], g.pitch, g.h, ADV_WW, ADV_WH, &A.tm[f])) return r;
+    for (int f = 0; f < NF; ++f)  // the windows are local rows; a.d0[] is indexed by global row
+        if (int r = field_tensor_map(a.d0[f] + (size_t)g.gy0 * g.pitch, g.pitch, g.h, ADV_WW, ADV_WH, &A.tm[f])) return r;
     if (UV == ADV_UV_TMA) {
         if (int r = field_tensor_map(u, g.pitch, g.h, ADV_TW, ADV_TH, &A.tm_u)) return r;
         if (int r = field_tensor_map(v, g.pitch, g.h, ADV_TW, ADV_TH, &A.tm_v)) return r;
     }
     A.a = a; A.u = u; A.v = v; A.g = g; A.dt0 = dt0; A.dt1 = dt1; A.xmax = xmax; A.ymax = ymax;
+    A.ly0 = ly0; A.ly1 = ly1;
     constexpr size_t smem = advect_tile_smem_bytes<NF, UV>();
     if (smem > 48 * 1024) {
         static std::atomic<uint64_t> attr_devices{0};
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
         if (!((attr_devices.load(std::memory_order_acquire) >> dev) & 1)) {
-            const cudaError_t e = cudaFuncSetAttribute(k_advect_tile<NF, UV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            const cudaError_t e = cudaFuncSetAttribute(k_advect_tile<NF, UV, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
             attr_devices.fetch_or(1ull << dev, std::memory_order_release);
         }
     }
-    const dim3 grid((g.w + ADV_TW - 1) / ADV_TW, (g.ny + ADV_TH - 1) / ADV_TH);
-    return (int)launch_pdl(true, k_advect_tile<NF, UV>, grid, dim3(256), smem, st, A);
+    const dim3 grid((g.w + ADV_TW - 1) / ADV_TW, (ly1 - ly0 + ADV_TH - 1) / ADV_TH);
+    return (int)launch_pdl(true, k_advect_tile<NF, UV, PASS>, grid, dim3(256), smem, st, A, tab);
 }
 
 }  // namespace fruid

@@ -171,20 +171,30 @@ static int op_advect(int nf, float* const* d, const float* const* d0, const int*
 #define FRUID_ADVECT(NF, PASS, name) \
     LAUNCH(name, st, launch_pdl(PASS != 2, k_advect4<NF, PASS>, (PASS == 2 ? dim3(296) : grid1), vec_block(), 0, st, a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, T))
     if (nf < 1 || nf > ADVECT_MAX_FIELDS || (multi && nf > 2)) return fail(FRUID_ERR_BAD_ARG, "advect: unsupported field count %d", nf);
-    if (!multi && ly0 == 1 && ly1 == g.h - 1 && advect_use_tile(g)) {
-        const bool self = (nf == 2 && d0[0] == u && d0[1] == v);  // lib.rs:204-205
+    if (advect_use_tile(g) && (multi ? nf <= 2 : (ly0 == 1 && ly1 == g.h - 1))) {
+        const bool selfadv = (nf == 2) && (d0[0] + (size_t)g.gy0 * g.pitch == u) && (d0[1] + (size_t)g.gy0 * g.pitch == v);  // lib.rs:204-205
         int r;
         prof_pre(st);
-        switch (nf) {
-            case 1: r = advect_tile_launch<1, ADV_UV_TMA>(a, u, v, g, dt0, dt1, xmax, ymax, st); break;
-            case 2: r = self ? advect_tile_launch<2, ADV_UV_SELF>(a, u, v, g, dt0, dt1, xmax, ymax, st)
-                             : advect_tile_launch<2, ADV_UV_TMA>(a, u, v, g, dt0, dt1, xmax, ymax, st); break;
-            case 3: r = advect_tile_launch<3, ADV_UV_LDG>(a, u, v, g, dt0, dt1, xmax, ymax, st); break;
-            default: r = advect_tile_launch<4, ADV_UV_LDG>(a, u, v, g, dt0, dt1, xmax, ymax, st); break;
+#define FRUID_ADVT(NF, UV, PASS) advect_tile_launch<NF, UV, PASS>(a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, T, st)
+        if (!multi) {
+            switch (nf) {
+                case 1: r = FRUID_ADVT(1, ADV_UV_TMA, 0); break;
+                case 2: r = selfadv ? FRUID_ADVT(2, ADV_UV_SELF, 0) : FRUID_ADVT(2, ADV_UV_TMA, 0); break;
+                case 3: r = FRUID_ADVT(3, ADV_UV_LDG, 0); break;
+                default: r = FRUID_ADVT(4, ADV_UV_LDG, 0); break;
+            }
+        } else {
+            if (nf == 1) r = FRUID_ADVT(1, ADV_UV_TMA, 1);
+            else r = selfadv ? FRUID_ADVT(2, ADV_UV_SELF, 1) : FRUID_ADVT(2, ADV_UV_TMA, 1);
         }
+#undef FRUID_ADVT
         if (r == -4) return fail(FRUID_ERR_CUDA, "advect: no tensor map for the gathered fields");
         static const char* const names[] = {"", "k_advect_tile_x1", "k_advect_tile_x2", "k_advect_tile_x3", "k_advect_tile_x4"};
         TRY(launched(names[nf], st));
+        if (multi) {  // pass 2: the quads that pass 1 queued, from the owners' memory
+            if (nf == 2) { FRUID_ADVECT(2, 2, "k_advect4x2_remote"); }
+            else { FRUID_ADVECT(1, 2, "k_advect4x1_remote"); }
+        }
     } else if (!multi) {
         switch (nf) {
             case 1: FRUID_ADVECT(1, 0, "k_advect4x1"); break;
