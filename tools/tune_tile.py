@@ -20,13 +20,14 @@ ap.add_argument("--cfgs", default="8x16,10x16,6x16,6x20,7x20,5x24,4x24,8x12,4x16
 ap.add_argument("--fused", default="1,2,4,6,10,20")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--modes", default="poisson,general,inviscid")
+ap.add_argument("--scale", type=float, default=1.0, help="magnitude of x and x0 (1e-35: below the range of the fused Poisson form)")
 args = ap.parse_args()
 
 w = h = args.size
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(1)
-x = torch.randn(h, w, device=dev, generator=g)
-x0 = torch.randn(h, w, device=dev, generator=g)
+x = torch.randn(h, w, device=dev, generator=g) * args.scale
+x0 = torch.randn(h, w, device=dev, generator=g) * args.scale
 s = torch.zeros(h, w, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 st = torch.cuda.current_stream()
