@@ -8,6 +8,6 @@ for c in scene250 scene128 inject1024 ksweep; do
 done
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/ev_${T}_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu --no-variants --sustain-seconds 0 > $O/ev_${T}_ncu_launch.log 2>&1; echo launches rc=$?
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:"k_jacobi_tile|k_divergence4|k_gradient4|k_advect4" -s 96 -c 16 \
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:"k_jacobi_tile|k_divergence4|k_gradient4|k_advect" -s 96 -c 16 \
   -f -o $O/ev_${T}_full python bench.py --steps 2 --warmup 3 --no-cpu --no-variants --sustain-seconds 0 > $O/ev_${T}_ncu_full.log 2>&1; echo full rc=$?
 ncu -i $O/ev_${T}_full.ncu-rep --page raw --csv > $O/ev_${T}_full.raw.csv 2>/dev/null

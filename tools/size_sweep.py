@@ -5,9 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, fruid_b200 as fb
 from fruid_b200 import _lib
 L = _lib.lib
-for n in (128, 250, 512, 1024, 2048, 4096, 8192, 16384):
-    if len(sys.argv) > 1 and str(n) not in sys.argv[1:]:
-        continue
+for n in ([int(a) for a in sys.argv[1:]] or [128, 250, 512, 1024, 2048, 4096, 8192, 16384]):
     sc = bench.make_scene(n, n)
     sim, den = fb.FluidSim(n, n), fb.DensitySim(n, n)
     for name, field in (("u", 0), ("v", 1), ("u_prev", 2), ("v_prev", 3)):
