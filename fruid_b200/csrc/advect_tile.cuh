@@ -204,21 +204,17 @@ __global__ void __launch_bounds__(256) k_advect_tile(const __grid_constant__ Adv
                 // a slab holds only its own rows: taps elsewhere are pass 2's business, load something harmless instead
                 if (PASS == 1 && !((t[c].j0 >= tab.my_lo) && (t[c].j0 + 1 < tab.my_hi))) q[c] = (size_t)j * g.pitch;
             }
-            float a00[NF][4], a10[NF][4], a01[NF][4], a11[NF][4];
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
+                float a00[4], a10[4], a01[4], a11[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const float* const p = A.a.d0[f] + q[c];
-                    a00[f][c] = __ldg(p); a10[f][c] = __ldg(p + 1); a01[f][c] = __ldg(p + g.pitch); a11[f][c] = __ldg(p + g.pitch + 1);
+                    a00[c] = __ldg(p); a10[c] = __ldg(p + 1); a01[c] = __ldg(p + g.pitch); a11[c] = __ldg(p + g.pitch + 1);
                 }
-            }
-            asm volatile("" ::: "memory");  // every gather load is issued before the first multiply waits for one
-#pragma unroll
-            for (int f = 0; f < NF; ++f) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
-                    r[f][c] = mixf(mixf(a00[f][c], a01[f][c], t[c].t1), mixf(a10[f][c], a11[f][c], t[c].t1), t[c].s1);
+                    r[f][c] = mixf(mixf(a00[c], a01[c], t[c].t1), mixf(a10[c], a11[c], t[c].t1), t[c].s1);
             }
         }
         bool own[4] = {true, true, true, true};
