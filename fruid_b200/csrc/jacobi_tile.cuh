@@ -212,13 +212,28 @@ static inline int jacobi_tile_default_fused(const Geom& g, int iters) {
     return T < 1 ? 1 : T;
 }
 
+// Grids of a few tiles per SM: the tile count quantises badly over 148 SMs (195 tiles of 128 x 140 at 1536^2 are two
+// rounds, the second a third full), and which shape wastes least depends on the size.  Measured 20-sweep Poisson solves
+// (tools/tune_tile.py --size; ms for 7x20 / this shape): 1536^2 0.054 / 0.048 (6x20), 2048^2 0.062 / 0.058 (8x16),
+// 3072^2 0.108 / 0.103 (10x16); from ~3500^2 on the default shape wins (4096^2: 8.7 rounds).
+static inline TileCfg jacobi_tile_midsize_shape(const Geom& g, const TileCfg& dflt) {
+    const size_t cells = (size_t)g.w * (size_t)g.h;
+    if (cells < (size_t)1800 * 1800) return TileCfg{6, 20};
+    if (cells < (size_t)2600 * 2600) return TileCfg{8, 16};
+    if (cells < (size_t)3500 * 3500) return TileCfg{10, 16};
+    return dflt;
+}
+
 // Shape for a launch of T fused sweeps.
 static inline TileCfg jacobi_tile_shape(const Geom& g, int T) {
     const TileKnobs K = tile_knobs();
     const TileCfg g_tile_cfg = K.cfg;
-    if (K.automatic && g.gh == g.h)
+    if (K.automatic && g.gh == g.h) {
         for (const TilePlan& p : kSmallGridPlans)
             if (T <= jacobi_tile_max_T(p.R, p.NW) && jacobi_tile_count(g, p.R, p.NW, T) <= 148) return TileCfg{p.R, p.NW};
+        const TileCfg m = jacobi_tile_midsize_shape(g, g_tile_cfg);
+        if (T <= jacobi_tile_max_T(m.R, m.NW)) return m;
+    }
     return g_tile_cfg;
 }
 

@@ -74,7 +74,11 @@ def test_automatic_shape_policy(L):
     assert plan(L, 250, 250)[1][:3] == [2, 16, 10]
     assert plan(L, 512, 512)[1][:3] == [3, 16, 10]
     assert plan(L, 1024, 1024)[1][:3] == [4, 24, 10]
-    for n in (1536, 2048, 4096, 16384):
+    # a few tiles per SM: the shape that quantises best over 148 SMs (measured per size, csrc/jacobi_tile.cuh)
+    assert plan(L, 1536, 1536)[1][:3] == [6, 20, 10]
+    assert plan(L, 2048, 2048)[1][:3] == [8, 16, 10]
+    assert plan(L, 3072, 3072)[1][:3] == [10, 16, 10]
+    for n in (4096, 16384):
         assert plan(L, n, n)[1][:3] == [7, 20, 10]
     # an explicit fused depth is respected (and moves to a shape that supports it)
     rc, p = plan(L, 250, 250, 20, 20)
