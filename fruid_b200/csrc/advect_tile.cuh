@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(256) k_advect_tile(const __grid_constant__ Adv
         fi[c] = (float)(i_first + 32 * c);
         col_ok[c] = (i_first + 32 * c >= 1) && (i_first + 32 * c <= g.nx);
     }
+    const bool deep = (PASS == 1) && (by0 + g.gy0 - ADV_MY >= tab.my_lo) && (by0 + g.gy0 + ADV_TH + ADV_MY < tab.my_hi);
     const int jw = by0 + wi * 4;                   // my first row
     const int nrows = min(4, A.ly1 - jw);          // warp-uniform
     // Window word of tap (i0, j0) = j0*ADV_WW + i0 - wbase (j0 a GLOBAL row); the centre cell (i, j) likewise.
@@ -218,7 +219,9 @@ __global__ void __launch_bounds__(256) k_advect_tile(const __grid_constant__ Adv
             }
         }
         bool own[4] = {true, true, true, true};
-        if (PASS == 1) {
+        // A block at least a window margin away from both slab cuts whose warp took the window path throughout has all
+        // its taps in owned rows ([j-3, j+4] around rows of the block): no vote needed (all but two block rows per rank).
+        if (PASS == 1 && !(deep && __all_sync(0xffffffffu, near))) {
             // k_advect4's pass 2 decides per thread = per quad of aligned columns [4q, 4q+4) (all of them, border and
             // padding columns of the field included) whether the quad's taps are all in rows this rank owns.
 #pragma unroll
