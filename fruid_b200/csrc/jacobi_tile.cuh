@@ -48,20 +48,37 @@ static bool recip_for(float c, RecipInfo* out, cudaStream_t st) {
     int e = 0;
     (void)frexpf(c, &e);
     if (c == c && c != 0.f && e > -30 && e < 30) {  // finite, normal, moderate magnitude
-        r.zh = 1.0f / c;
-        r.zl = (float)(1.0 / (double)c - (double)r.zh);
+        // Candidates, cheapest first: the two-instruction form q = fma(v, zh, v*zl) with the double-word reciprocal
+        // (zh, zl) -- correctly rounded for "almost all" c; when one significand in 2^23 rounds the wrong way, a
+        // neighbouring double-word (zl one ulp up or down, or zh one ulp off with zl re-derived) often has no failing
+        // significand at all -- then the three-instruction form with the nearest reciprocal.  Whatever is used has
+        // passed the exhaustive comparison with __fdiv_rn.
+        const float zh0 = 1.0f / c;
+        const double inv = 1.0 / (double)c;
+        struct Cand { int variant; float zh, zl; };
+        Cand cands[6];
+        int nc = 0;
+        const float zl0 = (float)(inv - (double)zh0);
+        cands[nc++] = {(int)MODE_RECIP, zh0, zl0};
+        cands[nc++] = {(int)MODE_RECIP, zh0, nextafterf(zl0, INFINITY)};
+        cands[nc++] = {(int)MODE_RECIP, zh0, nextafterf(zl0, -INFINITY)};
+        for (float dir : {INFINITY, -INFINITY}) {
+            const float zh1 = nextafterf(zh0, dir);
+            cands[nc++] = {(int)MODE_RECIP, zh1, (float)(inv - (double)zh1)};
+        }
+        cands[nc++] = {(int)MODE_RECIP3, zh0, zl0};
         // The check runs on the LAUNCHING stream (the caller made sure it is not capturing) and is followed by a
         // synchronisation of that stream only.
         int* bad = nullptr;
         if (cudaMalloc(&bad, sizeof(int)) == cudaSuccess) {
-            for (int variant : {(int)MODE_RECIP, (int)MODE_RECIP3}) {
+            for (int k = 0; k < nc; ++k) {
                 int h = 1;
                 if (cudaMemsetAsync(bad, 0, sizeof(int), st) != cudaSuccess) break;
-                k_recip_verify<<<(1u << 23) / 256, 256, 0, st>>>(c, r.zh, r.zl, variant, bad);
+                k_recip_verify<<<(1u << 23) / 256, 256, 0, st>>>(c, cands[k].zh, cands[k].zl, cands[k].variant, bad);
                 if (cudaMemcpyAsync(&h, bad, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
                 if (cudaStreamSynchronize(st) != cudaSuccess) break;
                 if (h == 0) {
-                    r.ok = true; r.mode = variant;
+                    r.ok = true; r.mode = cands[k].variant; r.zh = cands[k].zh; r.zl = cands[k].zl;
                     break;
                 }
             }

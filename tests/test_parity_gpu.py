@@ -976,7 +976,8 @@ def test_lin_solve_divisor_where_the_short_reciprocal_division_is_wrong(fb, O):
 
 
 # 1.670433402061462 = 1 + 4*(0.01*1e-6*4094*4094) in f32 (0x3fd5d0c3), the viscous 4096^2 bench divisor: the two-instruction
-# reciprocal division is wrong for one significand there, so the library must pick the three-instruction form
+# reciprocal division with the nearest double-word reciprocal is wrong for one significand there, so the library must pick
+# a neighbouring double-word that passes the exhaustive check, or the three-instruction form
 @pytest.mark.parametrize("c", [1.6704, 3.924, 1.0000001, 7.3e-3, 513.77, 1.9999999, 1.670433402061462])
 def test_lin_solve_general_divisor_extreme_values(fb, O, c):
     """General c takes the verified reciprocal division (MODE_RECIP) with a per-element IEEE fallback outside
