@@ -767,6 +767,34 @@ def run_e2e_frames(args, fb, torch, wl):
     return out
 
 
+def pin_to_gpu_numa(torch, local):
+    """Run this rank's host thread -- and therefore first-touch its host buffers -- on the NUMA node its GPU hangs off
+    (sysfs: the PCI device's numa_node and that node's cpulist, intersected with the CPUs this process may use).
+    Returns what was found, for the e2e line; a container that exposes one node only has nothing to choose."""
+    info = {"gpu_numa_node": None, "cpus_allowed": None, "cpus_on_gpu_node": None, "pinned": False}
+    try:
+        allowed = os.sched_getaffinity(0)
+        info["cpus_allowed"] = len(allowed)
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        info["gpu_numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        mine = cpus & allowed
+        info["cpus_on_gpu_node"] = len(mine)
+        if mine and mine != allowed:
+            os.sched_setaffinity(0, mine)
+            info["pinned"] = True
+    except Exception as e:  # no sysfs, no such attribute: leave the scheduler alone
+        info["error"] = f"{type(e).__name__}: {e}"[:120]
+    return info
+
+
 def run_b200_multi(args, wl, fb, dist, rank, world, local):
     """N GPUs of one node, one process per GPU: the scene is y-slab decomposed (rank r owns rows
     [r*h/N, (r+1)*h/N) plus 22 halo rows of each neighbour); halo rows and advection gathers move
@@ -779,6 +807,7 @@ def run_b200_multi(args, wl, fb, dist, rank, world, local):
     from fruid_b200.dist import SlabDensitySim, SlabFluidSim
     L = _lib.lib
     w, h = wl.w, wl.h
+    numa = pin_to_gpu_numa(torch, local)   # before any host buffer of this rank is touched
     steps = args.steps if args.steps is not None else 100
     sim = SlabFluidSim(w, h, rank, world)
     dens = [SlabDensitySim(w, h, rank, world) for _ in range(wl.dyes)]
@@ -903,12 +932,14 @@ def run_b200_multi(args, wl, fb, dist, rank, world, local):
         my_h2d = 4 * rows * w * 4 / (time.perf_counter() - t0) / 1e9
         all_h2d = [None] * world
         dist.all_gather_object(all_h2d, round(my_h2d, 2))
+        all_numa = [None] * world
+        dist.all_gather_object(all_numa, numa)
         for a in pinned:
             L.fruid_host_unregister(a.ctypes.data)
         e2e = {"value": res["pipelined"], "unit": "cell-steps/s", "h2d_bytes_per_step": 3 * w * h * 4,
                "d2h_bytes_per_step": w * h * 4, "steps": n, "serial_value": res["serial"],
                "pinned_host": len(pinned) == len(arrays), "per_rank_h2d_gbs_all_ranks_copying": all_h2d,
-               "pcie_ceiling_cell_steps_per_s": sum(all_h2d) * 1e9 / 16.0,
+               "pcie_ceiling_cell_steps_per_s": sum(all_h2d) * 1e9 / 16.0, "numa_per_rank": all_numa,
                "note": "whole-job bytes; each rank moves its own rows (h2d of 3 source fields, d2h of density) every step; "
                        "value = asynchronous (overlapped) transfers, serial_value = blocking upload/step/download; "
                        "pcie_ceiling = summed measured h2d rate / 16 B per cell-step (12 up + 4 down share the links): what "
