@@ -171,7 +171,11 @@ static int op_advect(int nf, float* const* d, const float* const* d0, const int*
 #define FRUID_ADVECT(NF, PASS, name) \
     LAUNCH(name, st, launch_pdl(PASS != 2, k_advect4<NF, PASS>, (PASS == 2 ? dim3(296) : grid1), vec_block(), 0, st, a, u, v, g, dt0, dt1, xmax, ymax, ly0, ly1, T))
     if (nf < 1 || nf > ADVECT_MAX_FIELDS || (multi && nf > 2)) return fail(FRUID_ERR_BAD_ARG, "advect: unsupported field count %d", nf);
-    if (advect_use_tile(g) && (multi ? nf <= 2 : (ly0 == 1 && ly1 == g.h - 1))) {
+    // TMA needs 16-byte aligned bases and row pitches (true for library-owned fields; the fruid_dev_* entry points take
+    // the caller's arrays as they come -- those fall back to the gather kernel instead of failing)
+    bool tma_ok = (g.pitch % 4 == 0) && ((uintptr_t)u % 16 == 0) && ((uintptr_t)v % 16 == 0);
+    for (int f = 0; f < nf; ++f) tma_ok = tma_ok && ((uintptr_t)d0[f] % 16 == 0);
+    if (tma_ok && advect_use_tile(g) && (multi ? nf <= 2 : (ly0 == 1 && ly1 == g.h - 1))) {
         const bool selfadv = (nf == 2) && (d0[0] + (size_t)g.gy0 * g.pitch == u) && (d0[1] + (size_t)g.gy0 * g.pitch == v);  // lib.rs:204-205
         int r;
         prof_pre(st);

@@ -157,6 +157,29 @@ def test_scene_steps_with_either_advect_kernel(fb, oracle_mod, w, h, visc, n, ad
         assert_bits(d.density().numpy(), od.dens, f"dens{i}")
 
 
+@pytest.mark.parametrize("w,h", [(256, 96), (1284, 515)])
+def test_device_pointer_advect(fb, O, w, h, advect_kernel):
+    """fruid_dev_advect: the caller's device arrays (here torch tensors, rows of `pitch` floats) on the caller's stream."""
+    import torch
+    rng = np.random.default_rng(w)
+    pitch = w + 12                                    # pitch % 4 == 0, rows longer than the field
+    host = {k: rand_field(rng, w, h, 1.0 if k.startswith("d") else 0.02) for k in ("d", "d0", "u", "v")}
+    dev = {}
+    for k, a in host.items():
+        t = torch.zeros((h, pitch), dtype=torch.float32, device="cuda")
+        t[:, :w] = torch.from_numpy(a).cuda()
+        dev[k] = t
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())  # the fills above run on the current stream
+    with torch.cuda.stream(st):
+        fb._lib.check(fb._lib.lib.fruid_dev_advect(NEGX, dev["d"].data_ptr(), dev["d0"].data_ptr(), dev["u"].data_ptr(),
+                                                   dev["v"].data_ptr(), w, h, pitch, 0.1, st.cuda_stream))
+    st.synchronize()
+    want = host["d"].copy()
+    O.fruid_oracle_advect(NEGX, want, host["d0"], host["u"], host["v"], w, h, 0.1, 1)
+    assert_bits(dev["d"][:, :w].cpu().numpy(), want)
+
+
 def test_advect_aliased_like_velocity_self_advection(fb, O, advect_kernel):
     """lib.rs:204: advect(NegX, u, u0, u0, v0, dt) -- d0 aliases u."""
     w, h = 130, 70
